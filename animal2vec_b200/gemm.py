@@ -1,0 +1,243 @@
+"""Host-side launchers for the tcgen05 GEMM (``a2v_gemm`` in include/a2v_capi.h).
+
+Everything that is a matrix product on the pretraining path goes through here:
+linear layers, (grouped) stride-1 convolutions expressed as a tap loop over shifted
+TMA tiles, and the weight-gradient reductions. Operands are bf16 tensors; outputs are
+bf16 or fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+
+def _operand(t: torch.Tensor, dim0: int, dim1: int, dim2: int, stride1: int, stride2: int) -> L.Operand:
+    if t.dtype != torch.bfloat16:
+        raise L.A2VError(f"GEMM operands must be bfloat16, got {t.dtype}")
+    return L.Operand(t.data_ptr(), dim0, dim1, dim2, stride1, stride2)
+
+
+def _pick_block_n(n: int) -> int:
+    if n <= 64:
+        return 64
+    if n <= 128:
+        return 128
+    return 256 if n % 256 == 0 or n > 512 else 128
+
+
+def _launch(d: L.GemmDesc, anchor: torch.Tensor) -> None:
+    L.require_device(anchor)
+    L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm")
+
+
+def _rows2d(t: torch.Tensor) -> tuple[int, int, int]:
+    """(rows, cols, row_stride) of a tensor viewed as a row-major matrix over its last dim."""
+    cols = t.shape[-1]
+    rows = t.numel() // cols
+    if t.dim() >= 2:
+        t2 = t.reshape(rows, cols) if t.is_contiguous() else t
+        if t2.dim() != 2:
+            raise L.A2VError("non-contiguous operand with more than 2 dims")
+        if t2.stride(1) != 1:
+            raise L.A2VError("operand inner dimension must be contiguous")
+        return rows, cols, t2.stride(0)
+    return rows, cols, cols
+
+
+def gemm_nt(
+    a: torch.Tensor,
+    w: torch.Tensor,
+    *,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    bias: Optional[torch.Tensor] = None,
+    act: int = 0,
+    preact: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    dgelu_u: Optional[torch.Tensor] = None,
+    alpha: float = 1.0,
+    accumulate: bool = False,
+    block_n: Optional[int] = None,
+) -> torch.Tensor:
+    """out[m, n] = alpha * sum_k a[m, k] * w[n, k] (+bias[n]) -> GELU -> *GELU'(u) -> +residual.
+
+    ``a``: (..., K) bf16, ``w``: (N, K) bf16 (nn.Linear weight layout).
+    """
+    m, k, lda = _rows2d(a)
+    n, kw, ldb = _rows2d(w)
+    if kw != k:
+        raise L.A2VError(f"gemm_nt: K mismatch {k} vs {kw}")
+    if out is None:
+        out = torch.empty(*a.shape[:-1], n, device=a.device, dtype=out_dtype or torch.bfloat16)
+    _, nc, ldc = _rows2d(out)
+    assert nc == n
+    for aux in (preact, residual, dgelu_u):
+        if aux is not None:
+            assert aux.dtype == out.dtype and aux.shape == out.shape and aux.is_contiguous() and out.is_contiguous()
+    d = L.GemmDesc()
+    d.mode = 0
+    d.block_n = block_n or _pick_block_n(n)
+    d.a = _operand(a, k, m, 1, lda, 0)
+    d.b = _operand(w, k, n, 1, ldb, 0)
+    d.M, d.N, d.k_per_tap, d.taps, d.batch, d.groups = m, n, k, 1, 1, 1
+    d.k_splits = 1
+    d.c = out.data_ptr()
+    d.c_dtype = L.dtype_code(out)
+    d.out_accumulate = 1 if accumulate else 0
+    d.ldc = ldc
+    d.alpha = alpha
+    d.bias = bias.data_ptr() if bias is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == n
+    d.act = act
+    d.preact = preact.data_ptr() if preact is not None else None
+    d.residual = residual.data_ptr() if residual is not None else None
+    d.dgelu_u = dgelu_u.data_ptr() if dgelu_u is not None else None
+    _launch(d, a)
+    return out
+
+
+def conv_nt(
+    x: torch.Tensor,
+    w: torch.Tensor,
+    *,
+    taps: int,
+    pad: int,
+    groups: int = 1,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: Optional[torch.dtype] = None,
+    bias: Optional[torch.Tensor] = None,
+    accumulate: bool = False,
+    block_n: Optional[int] = None,
+) -> torch.Tensor:
+    """Stride-1 (grouped) conv1d over channels-last activations without im2col.
+
+    ``x``: (B, T, G*Cg) bf16; ``w``: (G*Ng, taps*Cg) bf16 with the tap index major and the
+    in-group channel minor; returns (B, T, G*Ng):
+        y[b, t, g*Ng + n] = sum_{j, c} x[b, t + j - pad, g*Cg + c] * w[g*Ng + n, j*Cg + c].
+    Rows outside [0, T) read as zeros (TMA bounds check) = zero padding.
+    """
+    bsz, t, cin = x.shape
+    assert x.is_contiguous() and w.is_contiguous()
+    cg = cin // groups
+    nout = w.shape[0]
+    ng = nout // groups
+    assert w.shape[1] == taps * cg, (w.shape, taps, cg)
+    assert cg % 64 == 0 or taps == 1
+    if out is None:
+        out = torch.empty(bsz, t, nout, device=x.device, dtype=out_dtype or torch.bfloat16)
+    assert out.is_contiguous()
+    d = L.GemmDesc()
+    d.mode = 0
+    d.block_n = block_n or _pick_block_n(ng)
+    d.a = _operand(x, cin, t, bsz, cin, t * cin)
+    d.b = _operand(w, taps * cg, nout, 1, taps * cg, 0)
+    d.M, d.N, d.k_per_tap, d.taps, d.batch, d.groups = t, ng, cg, taps, bsz, groups
+    d.a_group_stride, d.a_row_off, d.a_tap_rows = cg, -pad, 1
+    d.b_group_stride = ng
+    d.k_splits = 1
+    d.c = out.data_ptr()
+    d.c_dtype = L.dtype_code(out)
+    d.out_accumulate = 1 if accumulate else 0
+    d.ldc = nout
+    d.c_batch_stride = t
+    d.c_group_stride = ng
+    d.alpha = 1.0
+    d.bias = bias.data_ptr() if bias is not None else None
+    _launch(d, x)
+    return out
+
+
+def _pick_splits(tiles: int, kblocks: int) -> int:
+    sms = 148
+    if tiles >= sms:
+        return 1
+    want = max(1, (2 * sms) // max(tiles, 1))
+    want = min(want, max(1, kblocks // 4))
+    per = -(-kblocks // want)
+    return -(-kblocks // per)
+
+
+def gemm_tn(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    alpha: float = 1.0,
+    k_splits: Optional[int] = None,
+    block_n: Optional[int] = None,
+) -> torch.Tensor:
+    """out[m, n] += alpha * sum_r a[r, m] * b[r, n]  (fp32 ``out``, atomically accumulated).
+
+    ``a``: (R, M) bf16, ``b``: (R, N) bf16 -- the weight-gradient product dY^T X.
+    """
+    r, m, lda = _rows2d(a)
+    r2, n, ldb = _rows2d(b)
+    assert r == r2 and out.dtype == torch.float32 and out.is_contiguous()
+    assert out.shape[-2:] == (m, n) or out.numel() == m * n
+    d = L.GemmDesc()
+    d.mode = 1
+    d.block_n = block_n or _pick_block_n(n)
+    d.a = _operand(a, m, r, 1, lda, 0)
+    d.b = _operand(b, n, r, 1, ldb, 0)
+    d.M, d.N, d.taps, d.batch, d.groups = m, n, 1, 1, 1
+    d.red_rows = r
+    tiles = -(-m // 128) * -(-n // d.block_n)
+    kblocks = -(-r // 64)
+    ks = k_splits or _pick_splits(tiles, kblocks)
+    per = -(-kblocks // ks)
+    d.k_splits = -(-kblocks // per)
+    d.c = out.data_ptr()
+    d.c_dtype = L.F32
+    d.out_atomic = 1
+    d.ldc = n
+    d.alpha = alpha
+    _launch(d, a)
+    return out
+
+
+def conv_wgrad_tn(
+    dy: torch.Tensor,
+    x: torch.Tensor,
+    out: torch.Tensor,
+    *,
+    taps: int,
+    pad: int,
+    groups: int = 1,
+    k_splits: Optional[int] = None,
+) -> torch.Tensor:
+    """Weight gradient of :func:`conv_nt`, atomically accumulated into fp32 ``out`` (G*Ng, taps*Cg):
+        out[g*Ng + n, j*Cg + c] += sum_{b, t} dy[b, t, g*Ng + n] * x[b, t + j - pad, g*Cg + c].
+    """
+    bsz, t, cin = x.shape
+    nout = dy.shape[-1]
+    cg, ng = cin // groups, nout // groups
+    assert dy.shape[:2] == x.shape[:2] and dy.is_contiguous() and x.is_contiguous()
+    assert out.dtype == torch.float32 and out.shape == (nout, taps * cg) and out.is_contiguous()
+    d = L.GemmDesc()
+    d.mode = 1
+    d.block_n = 64 if cg <= 64 else (128 if cg <= 128 else 256)
+    d.a = _operand(dy, nout, t, bsz, nout, t * nout)
+    d.b = _operand(x, cin, t, bsz, cin, t * cin)
+    d.M, d.N, d.taps, d.batch, d.groups = ng, cg, taps, bsz, groups
+    d.a_group_stride = ng
+    d.b_group_stride, d.b_row_off, d.b_tap_rows = cg, -pad, 1
+    d.red_rows = t
+    tiles = -(-ng // 128) * -(-cg // d.block_n) * taps * groups
+    kblocks = bsz * -(-t // 64)
+    ks = k_splits or _pick_splits(tiles, kblocks)
+    per = -(-kblocks // ks)
+    d.k_splits = -(-kblocks // per)
+    d.c = out.data_ptr()
+    d.c_dtype = L.F32
+    d.out_atomic = 1
+    d.ldc = taps * cg
+    d.c_group_stride = ng
+    d.c_tap_stride = cg
+    d.alpha = 1.0
+    _launch(d, x)
+    return out

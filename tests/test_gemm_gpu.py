@@ -1,0 +1,104 @@
+"""GPU parity of the tcgen05 GEMM against fp32 torch math on the same bf16-rounded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).norm() / (b.norm() + 1e-20)).item()
+
+
+def _randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize(
+    "m,n,k,bn",
+    [(128, 128, 64, 128), (256, 256, 512, 128), (1000, 384, 264, 128), (777, 1024, 1024, 256), (4096, 64, 128, 64),
+     (300, 200, 72, 256), (2048, 3072, 1024, 256)],
+)
+def test_gemm_nt_plain(m, n, k, bn):
+    from animal2vec_b200 import gemm
+
+    a, w = _randn(m, k, seed=1), _randn(n, k, seed=2)
+    ref = a.float() @ w.float().t()
+    out = gemm.gemm_nt(a, w, out_dtype=torch.float32, block_n=bn)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+    out16 = gemm.gemm_nt(a, w, block_n=bn)
+    assert _rel(out16, ref) < 4e-3
+
+
+def test_gemm_nt_epilogues():
+    from animal2vec_b200 import gemm
+
+    m, n, k = 515, 320, 256
+    a, w = _randn(m, k, seed=3), _randn(n, k, scale=0.1, seed=4)
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda")
+    u_ref = a.float() @ w.float().t() * 0.5 + bias
+    pre = torch.empty(m, n, device="cuda")
+    out = gemm.gemm_nt(a, w, out_dtype=torch.float32, bias=bias, act=1, preact=pre, residual=res, alpha=0.5)
+    assert _rel(pre, u_ref) < 1e-5
+    assert _rel(out, F.gelu(u_ref) + res) < 1e-5
+    # dgelu epilogue: out = (a w^T) * gelu'(u)
+    u = torch.randn(m, n, device="cuda")
+    out2 = gemm.gemm_nt(a, w, out_dtype=torch.float32, dgelu_u=u)
+    uu = u.clone().requires_grad_(True)
+    F.gelu(uu).sum().backward()
+    assert _rel(out2, (a.float() @ w.float().t()) * uu.grad) < 1e-5
+    # accumulate
+    acc = torch.ones(m, n, device="cuda")
+    gemm.gemm_nt(a, w, out=acc, accumulate=True)
+    assert _rel(acc, 1 + a.float() @ w.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize("bsz,t,cg,ng,groups,taps", [(2, 300, 64, 64, 4, 19), (3, 130, 64, 64, 2, 7), (1, 257, 128, 192, 1, 3),
+                                                    (2, 2000, 64, 64, 16, 19)])
+def test_conv_nt(bsz, t, cg, ng, groups, taps):
+    from animal2vec_b200 import gemm
+
+    pad = taps // 2
+    x = _randn(bsz, t, groups * cg, seed=5)
+    wt = _randn(groups * ng, cg, taps, scale=0.05, seed=6)  # torch layout (out, in/groups, k)
+    bias = torch.randn(groups * ng, device="cuda")
+    ref = F.conv1d(x.float().transpose(1, 2), wt.float(), bias, padding=pad, groups=groups).transpose(1, 2)
+    w = wt.permute(0, 2, 1).reshape(groups * ng, taps * cg).contiguous()
+    out = gemm.conv_nt(x, w, taps=taps, pad=pad, groups=groups, out_dtype=torch.float32, bias=bias)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+
+
+@pytest.mark.parametrize("r,m,n,bn,ks", [(64, 128, 128, 128, 1), (1000, 256, 320, 128, None), (5000, 1024, 512, 256, None),
+                                         (333, 104, 64, 64, 3), (4096, 128, 4096, 256, 1)])
+def test_gemm_tn(r, m, n, bn, ks):
+    from animal2vec_b200 import gemm
+
+    a, b = _randn(r, m, seed=7), _randn(r, n, seed=8)
+    ref = a.float().t() @ b.float()
+    out = torch.zeros(m, n, device="cuda")
+    gemm.gemm_tn(a, b, out, block_n=bn, k_splits=ks)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+    gemm.gemm_tn(a, b, out, block_n=bn, k_splits=ks)  # accumulates
+    assert _rel(out, 2 * ref) < 1e-5
+
+
+@pytest.mark.parametrize("bsz,t,cg,ng,groups,taps", [(2, 300, 64, 64, 4, 19), (3, 130, 64, 64, 2, 7), (2, 257, 128, 128, 1, 3)])
+def test_conv_wgrad_tn(bsz, t, cg, ng, groups, taps):
+    from animal2vec_b200 import gemm
+
+    pad = taps // 2
+    x = _randn(bsz, t, groups * cg, seed=9)
+    dy = _randn(bsz, t, groups * ng, seed=10)
+    xt = x.float().transpose(1, 2).requires_grad_(False)
+    wt = torch.zeros(groups * ng, cg, taps, device="cuda", requires_grad=True)
+    y = F.conv1d(xt, wt, None, padding=pad, groups=groups)
+    y.backward(dy.float().transpose(1, 2))
+    ref = wt.grad.permute(0, 2, 1).reshape(groups * ng, taps * cg)
+    out = torch.zeros(groups * ng, taps * cg, device="cuda")
+    gemm.conv_wgrad_tn(dy, x, out, taps=taps, pad=pad, groups=groups)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
