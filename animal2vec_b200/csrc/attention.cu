@@ -1,0 +1,631 @@
+// Multi-head self-attention with on-the-fly ALiBi (head dim 64).
+//
+// Reference behaviour replaced (file:line under /root/reference):
+//   nn/modalities/modules.py:368-410 AltAttention.forward: q*scale @ k^T, + alibi bias (fp32),
+//     softmax fp32, dropout, @ v.
+//   nn/modalities/base.py:553-698 get_alibi / get_alibi_bias / masked_alibi and base.py:293-314
+//     (per-head learned scale, clamp_min 0, clone repeat, double gather by ids_keep): the
+//     (B*M, H, T, T) fp32 bias tensor is never built; bias[h,i,j] = -slope_h*max(scale_h,0)*|pos_i-pos_j|
+//     is evaluated from the token positions inside the kernels.
+//
+// Kernels:
+//   attn_fwd_tcgen05_kernel : bf16, flash-style. S = Q K^T and O_j = P V_j run on tcgen05 with
+//                             TMEM accumulators, Q/K/V tiles arrive by TMA, one thread per query row
+//                             does the online softmax straight out of TMEM (no shuffles).
+//   attn_bwd_wmma_kernel    : bf16, student shapes (L <= 160 kept tokens): whole head resident in
+//                             shared memory, mma.sync via wmma.
+//   attn_*_ref_kernel       : fp32 CUDA-core kernels for the fp32 validation mode.
+#include <mma.h>
+#include "common.cuh"
+#include "../../include/a2v_capi.h"
+
+namespace a2v {
+
+constexpr int HD = 64;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+    const void* qkv;
+    void* out;
+    float* lse;
+    const int* pos;
+    const float* slopes;
+    const float* alibi_scale;
+    int alibi_scale_stride;
+    int batch, L, H, D;
+    float sm_scale;
+    float drop_p;
+    unsigned long long seed;
+    const void* dout;
+    void* dqkv;
+    float* dalibi_scale;
+};
+
+__device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
+    float sc = 1.0f;
+    if (p.alibi_scale != nullptr) sc = fmaxf(p.alibi_scale[h * p.alibi_scale_stride], 0.f);
+    return p.slopes != nullptr ? p.slopes[h] * sc : 0.f;
+}
+
+__device__ __forceinline__ bool attn_keep(unsigned long long seed, long long bh, int L, int i, int j, float pd) {
+    const unsigned long long stride4 = (unsigned long long)((L + 3) >> 2);
+    const uint64_t hsh = rng64(seed, ((unsigned long long)bh * L + i) * stride4 + (j >> 2));
+    const uint32_t thr = (uint32_t)(pd * 65536.0f);
+    return ((uint32_t)(hsh >> (16 * (j & 3))) & 0xffffu) >= thr;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward, tcgen05
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_SMEM_Q = 0;
+constexpr int ATT_SMEM_K = 16384;             // 2 buffers
+constexpr int ATT_SMEM_V = 16384 * 3;         // 2 buffers
+constexpr int ATT_SMEM_P = 16384 * 5;         // 2 chunks of 64 keys
+constexpr int ATT_SMEM_POS = 16384 * 7;       // 2 x 128 ints
+constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 1024;
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(128, 2)
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
+    uint64_t* bar_q = bars;
+    uint64_t* bar_kv = bars + 1;  // [2]
+    uint64_t* bar_s = bars + 3;
+    uint64_t* bar_o = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    int* spos = reinterpret_cast<int*>(smem + ATT_SMEM_POS);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int L = p.L, D = p.D;
+    const int n_kv = (L + 127) >> 7;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tm);
+        mbar_init(bar_q, 1);
+        mbar_init(&bar_kv[0], 1);
+        mbar_init(&bar_kv[1], 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_o, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base;        // 128 columns
+    const uint32_t tmem_o = tmem_base + 128;  // 64 columns
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+
+    if (tid == 0) {
+        mbar_expect_tx(bar_q, 16384);
+        tma_load_3d(smem + ATT_SMEM_Q, &tm, bar_q, h * HD, q0, b);
+        mbar_expect_tx(&bar_kv[0], 32768);
+        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_kv[0], D + h * HD, 0, b);
+        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_kv[0], 2 * D + h * HD, 0, b);
+    }
+
+    const int qi = q0 + tid;  // this thread's query row
+    const bool q_ok = qi < L;
+    const int pos_i = q_ok ? (p.pos != nullptr ? p.pos[(long long)b * L + qi] : qi) : 0;
+    const float coef2 = head_coef(p, h) * LOG2E;
+    const float scale2 = p.sm_scale * LOG2E;
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const long long bh = (long long)b * p.H + h;
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float o_acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
+
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+
+    for (int j = 0; j < n_kv; ++j) {
+        const int buf = j & 1;
+        const int k0 = j * 128;
+        {
+            const int kj = k0 + tid;
+            spos[buf * 128 + tid] = kj < L ? (p.pos != nullptr ? p.pos[(long long)b * L + kj] : kj) : -(1 << 28);
+        }
+        if (tid == 0) {
+            if (j + 1 < n_kv) {
+                mbar_expect_tx(&bar_kv[buf ^ 1], 32768);
+                tma_load_3d(smem + ATT_SMEM_K + (buf ^ 1) * 16384, &tm, &bar_kv[buf ^ 1], D + h * HD, k0 + 128, b);
+                tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_kv[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
+            }
+            if (j == 0) mbar_wait(bar_q, 0);
+            mbar_wait(&bar_kv[buf], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(smem + ATT_SMEM_Q);
+            const uint32_t ka = smem_u32(smem + ATT_SMEM_K + buf * 16384);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+                umma_bf16(tmem_s, umma_smem_desc(qa + k * 32, 0, 1024), umma_smem_desc(ka + k * 32, 0, 1024), idesc_s,
+                          k > 0 ? 1u : 0u);
+            umma_commit(bar_s);
+        }
+        __syncthreads();  // spos visible
+        mbar_wait(bar_s, j & 1);
+        tc_fence_after();
+
+        // pass 1: row maximum
+        float m_tile = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pk = spos[buf * 128 + c * 32 + i];
+                const float t = __uint_as_float(raw[i]) * scale2 - coef2 * fabsf((float)(pos_i - pk));
+                m_tile = fmaxf(m_tile, pk >= 0 ? t : -INFINITY);
+            }
+        }
+        const float m_new = fmaxf(m_run, m_tile);
+        const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
+        float l_tile = 0.f;
+        // pass 2: probabilities -> shared memory (bf16, 128B-swizzled K-major A operand)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
+            tmem_ld_wait();
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int pk = spos[buf * 128 + c * 32 + i];
+                const float t = __uint_as_float(raw[i]) * scale2 - coef2 * fabsf((float)(pos_i - pk));
+                float e = pk >= 0 ? exp2f(t - m_new) : 0.f;
+                l_tile += e;
+                if (p.drop_p > 0.f) e = attn_keep(p.seed, bh, L, qi, k0 + c * 32 + i, p.drop_p) ? e * inv_keep : 0.f;
+                pv[i] = e;
+            }
+            // chunk c covers keys c*32..c*32+31 = 64-key half (c>>1), 16-byte units ((c&1)*4 .. +3)
+            uint8_t* prow = smem + ATT_SMEM_P + (c >> 1) * 16384 + tid * 128;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint4 v;
+                v.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]);
+                v.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
+                v.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]);
+                v.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
+                const int unit = ((c & 1) * 4 + u) ^ (tid & 7);
+                *reinterpret_cast<uint4*>(prow + unit * 16) = v;
+            }
+        }
+        l_run = l_run * alpha + l_tile;
+        m_run = m_new;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t pa = smem_u32(smem + ATT_SMEM_P);
+            const uint32_t va = smem_u32(smem + ATT_SMEM_V + buf * 16384);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_bf16(tmem_o, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
+                          umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+            umma_commit(bar_o);
+        }
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o_acc[d] *= alpha;
+        mbar_wait(bar_o, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_o + lane_off + c * 32, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
+        }
+        tc_fence_before();
+    }
+
+    if (q_ok) {
+        const float inv_l = 1.0f / l_run;
+        bf16* orow = reinterpret_cast<bf16*>(p.out) + ((long long)b * L + qi) * D + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            float v[4] = {o_acc[d] * inv_l, o_acc[d + 1] * inv_l, o_acc[d + 2] * inv_l, o_acc[d + 3] * inv_l};
+            store4(orow + d, v);
+        }
+        if (p.lse != nullptr) p.lse[bh * L + qi] = (m_run + log2f(l_run)) * LN2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, shared-memory resident head (student: L <= 160), wmma bf16
+// ------------------------------------------------------------------------------------------
+constexpr int BWD_LMAX = 160;
+constexpr int BWD_LD = 72;    // leading dimension of the (L x 64) operand tiles
+constexpr int BWD_SCR = 20;   // leading dimension of the fp32 16x16 scratch tiles
+
+__global__ void __launch_bounds__(256, 1) attn_bwd_wmma_kernel(const AttnParams p) {
+    using namespace nvcuda;
+    extern __shared__ __align__(128) uint8_t smem_b[];
+    const int L = p.L, D = p.D, h = blockIdx.x, b = blockIdx.y;
+    const int LP = (L + 15) & ~15;
+    const int ldp = LP + 8;
+    bf16* sQ = reinterpret_cast<bf16*>(smem_b);
+    bf16* sK = sQ + LP * BWD_LD;
+    bf16* sV = sK + LP * BWD_LD;
+    bf16* sdO = sV + LP * BWD_LD;
+    bf16* sPd = sdO + LP * BWD_LD;
+    bf16* sdS = sPd + LP * ldp;
+    float* scr = reinterpret_cast<float*>(sdS + LP * ldp);  // 8 warps x 2 x 16 x BWD_SCR
+    float* s_lse = scr + 8 * 2 * 16 * BWD_SCR;
+    float* s_delta = s_lse + LP;
+    int* s_pos = reinterpret_cast<int*>(s_delta + LP);
+    __shared__ float s_dc[8];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long bh = (long long)b * p.H + h;
+    const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
+    const bf16* dout = reinterpret_cast<const bf16*>(p.dout);
+    const bf16* outp = reinterpret_cast<const bf16*>(p.out);
+
+    // ---- stage 0: load operands (8 bf16 = 16 B per access), zero the padding rows
+    for (int e = tid; e < LP * 8; e += 256) {
+        const int i = e >> 3, c8 = (e & 7) * 8;
+        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, g = q;
+        if (i < L) {
+            const bf16* row = qkv + ((long long)b * L + i) * 3 * D + h * HD + c8;
+            q = *reinterpret_cast<const uint4*>(row);
+            k = *reinterpret_cast<const uint4*>(row + D);
+            v = *reinterpret_cast<const uint4*>(row + 2 * D);
+            g = *reinterpret_cast<const uint4*>(dout + ((long long)b * L + i) * D + h * HD + c8);
+        }
+        *reinterpret_cast<uint4*>(sQ + i * BWD_LD + c8) = q;
+        *reinterpret_cast<uint4*>(sK + i * BWD_LD + c8) = k;
+        *reinterpret_cast<uint4*>(sV + i * BWD_LD + c8) = v;
+        *reinterpret_cast<uint4*>(sdO + i * BWD_LD + c8) = g;
+    }
+    for (int i = tid; i < LP; i += 256) {
+        float dl = 0.f;
+        if (i < L) {
+            const bf16* go = dout + ((long long)b * L + i) * D + h * HD;
+            const bf16* oo = outp + ((long long)b * L + i) * D + h * HD;
+            for (int d = 0; d < HD; d += 4) {
+                float a[4], c[4];
+                load4(go + d, a);
+                load4(oo + d, c);
+                dl += a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
+            }
+            s_lse[i] = p.lse[bh * L + i];
+            s_pos[i] = p.pos != nullptr ? p.pos[(long long)b * L + i] : i;
+        } else {
+            s_lse[i] = 0.f;
+            s_pos[i] = 0;
+        }
+        s_delta[i] = dl;
+    }
+    __syncthreads();
+
+    const float coef = head_coef(p, h);
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const int nt = LP >> 4;
+    float* scr_s = scr + warp * 2 * 16 * BWD_SCR;
+    float* scr_d = scr_s + 16 * BWD_SCR;
+    float dc_part = 0.f;
+
+    // ---- stage 1: S and dP tiles -> P*keep (bf16) and dS (bf16)
+    for (int tile = warp; tile < nt * nt; tile += 8) {
+        const int ti = tile / nt, tj = tile - ti * nt;
+        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc_s, acc_d;
+        wmma::fill_fragment(acc_s, 0.f);
+        wmma::fill_fragment(acc_d, 0.f);
+#pragma unroll
+        for (int k = 0; k < HD; k += 16) {
+            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> fb;
+            wmma::load_matrix_sync(fa, sQ + ti * 16 * BWD_LD + k, BWD_LD);
+            wmma::load_matrix_sync(fb, sK + tj * 16 * BWD_LD + k, BWD_LD);
+            wmma::mma_sync(acc_s, fa, fb, acc_s);
+            wmma::load_matrix_sync(fa, sdO + ti * 16 * BWD_LD + k, BWD_LD);
+            wmma::load_matrix_sync(fb, sV + tj * 16 * BWD_LD + k, BWD_LD);
+            wmma::mma_sync(acc_d, fa, fb, acc_d);
+        }
+        wmma::store_matrix_sync(scr_s, acc_s, BWD_SCR, wmma::mem_row_major);
+        wmma::store_matrix_sync(scr_d, acc_d, BWD_SCR, wmma::mem_row_major);
+        __syncwarp();
+        const int r = lane >> 1, c0 = (lane & 1) * 8;
+        const int i = ti * 16 + r;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int j = tj * 16 + c0 + cc;
+            float pd_ = 0.f, ds = 0.f;
+            if (i < L && j < L) {
+                const float dist = fabsf((float)(s_pos[i] - s_pos[j]));
+                const float s = scr_s[r * BWD_SCR + c0 + cc] * p.sm_scale - coef * dist;
+                const float pr = __expf(s - s_lse[i]);
+                float ks = 1.f;
+                if (p.drop_p > 0.f) ks = attn_keep(p.seed, bh, L, i, j, p.drop_p) ? inv_keep : 0.f;
+                const float dp = scr_d[r * BWD_SCR + c0 + cc] * ks;
+                ds = pr * (dp - s_delta[i]);
+                pd_ = pr * ks;
+                dc_part -= ds * dist;
+            }
+            sPd[i * ldp + j] = __float2bfloat16_rn(pd_);
+            sdS[i * ldp + j] = __float2bfloat16_rn(ds);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- stage 2: dV = Pd^T dO, dK = dS^T Q * scale, dQ = dS K * scale
+    bf16* dqkv = reinterpret_cast<bf16*>(p.dqkv);
+    for (int tile = warp; tile < 3 * nt * 4; tile += 8) {
+        const int which = tile / (nt * 4);  // 0 dQ, 1 dK, 2 dV
+        const int rem = tile - which * nt * 4;
+        const int tr = rem >> 2, tc = rem & 3;
+        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
+        wmma::fill_fragment(acc, 0.f);
+        for (int k = 0; k < LP; k += 16) {
+            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
+            if (which == 0) {
+                wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
+                wmma::load_matrix_sync(fa, sdS + tr * 16 * ldp + k, ldp);
+                wmma::load_matrix_sync(fb, sK + k * BWD_LD + tc * 16, BWD_LD);
+                wmma::mma_sync(acc, fa, fb, acc);
+            } else {
+                wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fa;
+                wmma::load_matrix_sync(fa, (which == 1 ? sdS : sPd) + k * ldp + tr * 16, ldp);
+                wmma::load_matrix_sync(fb, (which == 1 ? sQ : sdO) + k * BWD_LD + tc * 16, BWD_LD);
+                wmma::mma_sync(acc, fa, fb, acc);
+            }
+        }
+        wmma::store_matrix_sync(scr_s, acc, BWD_SCR, wmma::mem_row_major);
+        __syncwarp();
+        const int r = lane >> 1, c0 = (lane & 1) * 8;
+        const int i = tr * 16 + r;
+        if (i < L) {
+            const float sc = which == 2 ? 1.0f : p.sm_scale;
+            uint4 o;
+            o.x = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 0] * sc, scr_s[r * BWD_SCR + c0 + 1] * sc);
+            o.y = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 2] * sc, scr_s[r * BWD_SCR + c0 + 3] * sc);
+            o.z = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 4] * sc, scr_s[r * BWD_SCR + c0 + 5] * sc);
+            o.w = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 6] * sc, scr_s[r * BWD_SCR + c0 + 7] * sc);
+            *reinterpret_cast<uint4*>(dqkv + ((long long)b * L + i) * 3 * D + which * D + h * HD + tc * 16 + c0) = o;
+        }
+        __syncwarp();
+    }
+
+    // ---- stage 3: d(alibi_scale)
+    dc_part = warp_sum(dc_part);
+    if (lane == 0) s_dc[warp] = dc_part;
+    __syncthreads();
+    if (tid == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += s_dc[w];
+        if (p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
+            atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, s * p.slopes[h]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 validation-mode kernels (CUDA cores, one thread per query row)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attn_fwd_ref_kernel(const AttnParams p) {
+    const int L = p.L, D = p.D, h = blockIdx.y, b = blockIdx.z;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= L) return;
+    const float* qkv = reinterpret_cast<const float*>(p.qkv);
+    const long long bh = (long long)b * p.H + h;
+    const float coef = head_coef(p, h);
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    float q[HD], o[HD];
+    const float* qrow = qkv + ((long long)b * L + i) * 3 * D + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+        q[d] = qrow[d] * p.sm_scale;
+        o[d] = 0.f;
+    }
+    const int pi = p.pos != nullptr ? p.pos[(long long)b * L + i] : i;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+        const float* krow = qkv + ((long long)b * L + j) * 3 * D + D + h * HD;
+        float s = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) s += q[d] * krow[d];
+        const int pj = p.pos != nullptr ? p.pos[(long long)b * L + j] : j;
+        s -= coef * fabsf((float)(pi - pj));
+        const float mn = fmaxf(m, s);
+        const float al = __expf(m - mn);
+        float e = __expf(s - mn);
+        l = l * al + e;
+        if (p.drop_p > 0.f) e = attn_keep(p.seed, bh, L, i, j, p.drop_p) ? e * inv_keep : 0.f;
+        const float* vrow = krow + D;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = o[d] * al + e * vrow[d];
+        m = mn;
+    }
+    float* orow = reinterpret_cast<float*>(p.out) + ((long long)b * L + i) * D + h * HD;
+    const float inv = 1.0f / l;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) orow[d] = o[d] * inv;
+    if (p.lse != nullptr) p.lse[bh * L + i] = m + __logf(l);
+}
+
+// dqkv must be zero-initialised (dK / dV are accumulated with atomics)
+__global__ void __launch_bounds__(128) attn_bwd_ref_kernel(const AttnParams p) {
+    __shared__ float s_dc[4];
+    const int L = p.L, D = p.D, h = blockIdx.y, b = blockIdx.z;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const float* qkv = reinterpret_cast<const float*>(p.qkv);
+    float* dqkv = reinterpret_cast<float*>(p.dqkv);
+    const long long bh = (long long)b * p.H + h;
+    const float coef = head_coef(p, h);
+    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    float dc = 0.f;
+    if (i < L) {
+        float q[HD], go[HD], dq[HD];
+        const float* qrow = qkv + ((long long)b * L + i) * 3 * D + h * HD;
+        const float* gorow = reinterpret_cast<const float*>(p.dout) + ((long long)b * L + i) * D + h * HD;
+        const float* orow = reinterpret_cast<const float*>(p.out) + ((long long)b * L + i) * D + h * HD;
+        float delta = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) {
+            q[d] = qrow[d];
+            go[d] = gorow[d];
+            dq[d] = 0.f;
+            delta += go[d] * orow[d];
+        }
+        const float lse = p.lse[bh * L + i];
+        const int pi = p.pos != nullptr ? p.pos[(long long)b * L + i] : i;
+        for (int j = 0; j < L; ++j) {
+            const float* krow = qkv + ((long long)b * L + j) * 3 * D + D + h * HD;
+            const float* vrow = krow + D;
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                s += q[d] * krow[d];
+                dp += go[d] * vrow[d];
+            }
+            const int pj = p.pos != nullptr ? p.pos[(long long)b * L + j] : j;
+            const float dist = fabsf((float)(pi - pj));
+            const float pr = __expf(s * p.sm_scale - coef * dist - lse);
+            float ks = 1.f;
+            if (p.drop_p > 0.f) ks = attn_keep(p.seed, bh, L, i, j, p.drop_p) ? inv_keep : 0.f;
+            const float ds = pr * (dp * ks - delta);
+            dc -= ds * dist;
+            float* dk = dqkv + ((long long)b * L + j) * 3 * D + D + h * HD;
+            float* dv = dk + D;
+            const float pk = pr * ks;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) {
+                dq[d] += ds * krow[d];
+                atomicAdd(dk + d, ds * q[d] * p.sm_scale);
+                atomicAdd(dv + d, pk * go[d]);
+            }
+        }
+        float* dqrow = dqkv + ((long long)b * L + i) * 3 * D + h * HD;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) dqrow[d] = dq[d] * p.sm_scale;
+    }
+    dc = warp_sum(dc);
+    if ((threadIdx.x & 31) == 0) s_dc[threadIdx.x >> 5] = dc;
+    __syncthreads();
+    if (threadIdx.x == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr) {
+        const float s = s_dc[0] + s_dc[1] + s_dc[2] + s_dc[3];
+        if (p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
+            atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, s * p.slopes[h]);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
+    A2V_REQUIRE(d != nullptr, "attention: NULL descriptor");
+    A2V_REQUIRE(d->dtype == A2V_F32 || d->dtype == A2V_BF16, "attention: bad dtype");
+    A2V_REQUIRE(d->qkv && d->out, "attention: NULL qkv/out");
+    A2V_REQUIRE(d->batch > 0 && d->L > 0 && d->H > 0 && d->batch <= 65535 && d->H <= 65535,
+                "attention: bad extents batch=%d L=%d H=%d", d->batch, d->L, d->H);
+    A2V_REQUIRE(d->head_dim == HD, "attention: only head_dim 64 is supported (got %d)", d->head_dim);
+    A2V_REQUIRE(d->drop_p >= 0.f && d->drop_p < 1.f, "attention: bad dropout probability");
+    p.qkv = d->qkv; p.out = d->out; p.lse = d->lse; p.pos = d->pos;
+    p.slopes = d->slopes; p.alibi_scale = d->alibi_scale; p.alibi_scale_stride = d->alibi_scale_stride;
+    p.batch = d->batch; p.L = d->L; p.H = d->H; p.D = d->H * HD;
+    p.sm_scale = d->sm_scale; p.drop_p = d->drop_p; p.seed = d->seed;
+    p.dout = d->dout; p.dqkv = d->dqkv; p.dalibi_scale = d->dalibi_scale;
+    return A2V_OK;
+}
+
+}  // namespace a2v
+
+using namespace a2v;
+
+extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
+    AttnParams p;
+    int rc = validate_attn(d, p);
+    if (rc != A2V_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    dim3 grid(ceil_div(p.L, 128), p.H, p.batch);
+    if (d->dtype == A2V_F32) {
+        attn_fwd_ref_kernel<<<grid, 128, 0, st>>>(p);
+        return a2v_check_launch("attn_fwd_ref");
+    }
+    static EncodeTiledFn2 encode = nullptr;
+    if (encode == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym) {
+            a2v_set_error("attention: cuTensorMapEncodeTiled not available");
+            return A2V_ERR_CUDA;
+        }
+        encode = reinterpret_cast<EncodeTiledFn2>(sym);
+    }
+    A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0, "attention: qkv not 16-byte aligned");
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)(3 * p.D), (cuuint64_t)p.L, (cuuint64_t)p.batch};
+    cuuint64_t strides[2] = {(cuuint64_t)(3 * p.D) * 2, (cuuint64_t)p.L * 3 * p.D * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.qkv), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        a2v_set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return A2V_ERR_CUDA;
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             ATT_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            a2v_set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return A2V_ERR_CUDA;
+        }
+        configured = true;
+    }
+    attn_fwd_tcgen05_kernel<<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    return a2v_check_launch("attn_fwd_tcgen05");
+}
+
+extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
+    AttnParams p;
+    int rc = validate_attn(d, p);
+    if (rc != A2V_OK) return rc;
+    A2V_REQUIRE(d->dout && d->dqkv && d->lse, "attention backward: dout / dqkv / lse are required");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d->dtype == A2V_F32) {
+        dim3 grid(ceil_div(p.L, 128), p.H, p.batch);
+        attn_bwd_ref_kernel<<<grid, 128, 0, st>>>(p);
+        return a2v_check_launch("attn_bwd_ref");
+    }
+    A2V_REQUIRE(p.L <= BWD_LMAX,
+                "attention backward (bf16): the shared-memory-resident kernel supports at most %d tokens per "
+                "sequence, got %d", BWD_LMAX, p.L);
+    const int LP = (p.L + 15) & ~15;
+    const size_t smem = (size_t)4 * LP * BWD_LD * 2 + (size_t)2 * LP * (LP + 8) * 2 + 8 * 2 * 16 * BWD_SCR * 4 +
+                        (size_t)3 * LP * 4 + 128;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_wmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) {
+            a2v_set_error("attention backward: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+            return A2V_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    dim3 grid(p.H, p.batch);
+    attn_bwd_wmma_kernel<<<grid, 256, smem, st>>>(p);
+    return a2v_check_launch("attn_bwd_wmma");
+}

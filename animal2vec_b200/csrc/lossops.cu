@@ -1,0 +1,271 @@
+// Teacher-target construction and masked regression loss (HBM-bound).
+//
+// Reference behaviour replaced (file:line under /root/reference):
+//   nn/data2vec2.py:1023-1066 make_targets: per layer F.instance_norm over time (fp32, biased
+//     variance, eps 1e-5, no affine) of the top-K teacher FFN outputs, then the mean over layers
+//       -> a2v_target_stats + a2v_target_apply
+//   data2vec2.py:850-862,1005-1021: y.repeat_interleave(M)[mask], x[mask], MSE * D^-0.5
+//       -> a2v_d2v_loss_fwd / _bwd  (the cloned / gathered tensors are never materialised)
+//   data2vec2.py:1095-1110 compute_var (pred_var / target_var logging statistics)
+//       -> column sums accumulated in the same pass as the loss
+#include "common.cuh"
+#include "../../include/a2v_capi.h"
+
+namespace a2v {
+
+// stats[l][b][c] = (mean, rstd) over t of layer l. grid (D/128, B, K), 256 threads.
+template <typename T>
+__global__ void __launch_bounds__(256) target_stats_kernel(const void* const* __restrict__ layers,
+                                                           float2* __restrict__ stats, int B, int T_, int D,
+                                                           float eps) {
+    __shared__ float part[2][8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const int b = blockIdx.y, l = blockIdx.z;
+    const T* x = reinterpret_cast<const T*>(layers[l]) + (long long)b * T_ * D;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f}, shift[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < D) {
+        load4(x + c, shift);  // shifted sums: robust against mean^2 >> var cancellation
+        for (int t = warp; t < T_; t += 8) {
+            float v[4];
+            load4(x + (long long)t * D + c, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = v[j] - shift[j];
+                s1[j] += d;
+                s2[j] += d * d;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        part[0][warp][lane * 4 + j] = s1[j];
+        part[1][warp][lane * 4 + j] = s2[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < D) {
+            float a = 0.f, q = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                a += part[0][w][threadIdx.x];
+                q += part[1][w][threadIdx.x];
+            }
+            const float sh = to_f32(x[cc]);
+            const float m1 = a / (float)T_;
+            const float var = fmaxf(q / (float)T_ - m1 * m1, 0.f);
+            stats[((long long)l * B + b) * D + cc] = make_float2(sh + m1, rsqrtf(var + eps));
+        }
+    }
+}
+
+// y[b][t][c] = (1/K) sum_l (x_l[b][t][c] - mean) * rstd.  grid (D/128, B, row_splits)
+template <typename T>
+__global__ void __launch_bounds__(256) target_apply_kernel(const void* const* __restrict__ layers,
+                                                           const float2* __restrict__ stats, float* __restrict__ y,
+                                                           int K, int B, int T_, int D, int rows_per_block) {
+    extern __shared__ float2 sst[];  // [K][128]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 128;
+    const int b = blockIdx.y;
+    for (int i = threadIdx.x; i < K * 128; i += blockDim.x) {
+        const int l = i / 128, cc = c0 + (i % 128);
+        sst[i] = cc < D ? stats[((long long)l * B + b) * D + cc] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    const int c = c0 + lane * 4;
+    if (c >= D) return;
+    const int t0 = blockIdx.z * rows_per_block;
+    const int t1 = min(T_, t0 + rows_per_block);
+    const float invk = 1.0f / (float)K;
+    for (int t = t0 + warp; t < t1; t += 8) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const long long off = ((long long)b * T_ + t) * D + c;
+        for (int l = 0; l < K; ++l) {
+            float v[4];
+            load4(reinterpret_cast<const T*>(layers[l]) + off, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 st = sst[l * 128 + lane * 4 + j];
+                acc[j] += (v[j] - st.x) * st.y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] *= invk;
+        store4(y + off, acc);
+    }
+}
+
+// masked regression loss + logging statistics. grid (D/128, nblk)
+template <typename T>
+__global__ void __launch_bounds__(256) d2v_loss_fwd_kernel(const T* __restrict__ pred, const float* __restrict__ y,
+                                                           const uint8_t* __restrict__ mask, long long RT, int T_,
+                                                           int M, int D, float scale, long long rows_per_block,
+                                                           double* __restrict__ loss_sum,
+                                                           double* __restrict__ colstats) {
+    __shared__ float part[5][8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > RT) r1 = RT;
+    float sx[4] = {0, 0, 0, 0}, sxx[4] = {0, 0, 0, 0}, sy[4] = {0, 0, 0, 0}, syy[4] = {0, 0, 0, 0};
+    float loss = 0.f;
+    if (c < D) {
+        for (long long o = r0 + warp; o < r1; o += 8) {
+            if (mask[o] == 0) continue;
+            const long long r = o / T_;
+            const int t = (int)(o - r * T_);
+            float x[4], yy[4];
+            load4(pred + o * D + c, x);
+            load4(y + ((r / M) * T_ + t) * D + c, yy);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float d = x[j] - yy[j];
+                loss += d * d;
+                sx[j] += x[j];
+                sxx[j] += x[j] * x[j];
+                sy[j] += yy[j];
+                syy[j] += yy[j] * yy[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        part[0][warp][lane * 4 + j] = sx[j];
+        part[1][warp][lane * 4 + j] = sxx[j];
+        part[2][warp][lane * 4 + j] = sy[j];
+        part[3][warp][lane * 4 + j] = syy[j];
+    }
+    loss = warp_sum(loss);
+    if (lane == 0) part[4][warp][0] = loss;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < D) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) s += part[k][w][threadIdx.x];
+                atomicAdd(colstats + (long long)k * D + cc, (double)s);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += part[4][w][0];
+        atomicAdd(loss_sum, (double)s * (double)scale);
+    }
+}
+
+// dpred = mask ? 2 * scale * g * (pred - y) : 0
+template <typename T>
+__global__ void __launch_bounds__(256) d2v_loss_bwd_kernel(const T* __restrict__ pred, const float* __restrict__ y,
+                                                           const uint8_t* __restrict__ mask, T* __restrict__ dpred,
+                                                           long long RT, int T_, int M, int D, float coef,
+                                                           const float* __restrict__ gptr) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * 8;
+    const float g = coef * (gptr != nullptr ? *gptr : 1.0f);
+    for (long long o = warp0; o < RT; o += nwarps) {
+        const bool m = mask[o] != 0;
+        const long long r = o / T_;
+        const int t = (int)(o - r * T_);
+        for (int c = lane * 4; c < D; c += 128) {
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m) {
+                float x[4], yy[4];
+                load4(pred + o * D + c, x);
+                load4(y + ((r / M) * T_ + t) * D + c, yy);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = g * (x[j] - yy[j]);
+            }
+            store4(dpred + o * D + c, v);
+        }
+    }
+}
+
+}  // namespace a2v
+
+using namespace a2v;
+
+extern "C" int a2v_target_stats(int dtype, const void* const* layers_dev, int K, int B, int T, int D, float eps,
+                                float* stats, a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "target_stats: bad dtype");
+    A2V_REQUIRE(layers_dev && stats && K > 0 && B > 0 && T > 0 && D > 0 && D % 4 == 0, "target_stats: bad arguments");
+    dim3 grid(ceil_div(D, 128), B, K);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_F32)
+        target_stats_kernel<float><<<grid, 256, 0, st>>>(layers_dev, (float2*)stats, B, T, D, eps);
+    else
+        target_stats_kernel<bf16><<<grid, 256, 0, st>>>(layers_dev, (float2*)stats, B, T, D, eps);
+    return a2v_check_launch("target_stats");
+}
+
+extern "C" int a2v_target_apply(int dtype, const void* const* layers_dev, int K, int B, int T, int D,
+                                const float* stats, float* y, a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "target_apply: bad dtype");
+    A2V_REQUIRE(layers_dev && stats && y && K > 0 && K <= 64 && B > 0 && T > 0 && D > 0 && D % 4 == 0,
+                "target_apply: bad arguments (K <= 64)");
+    const int cblocks = ceil_div(D, 128);
+    int splits = (a2v_num_sms() * 4) / (cblocks * B);
+    if (splits < 1) splits = 1;
+    if (splits > ceil_div(T, 8)) splits = ceil_div(T, 8);
+    const int rpb = ceil_div(T, splits);
+    dim3 grid(cblocks, B, ceil_div(T, rpb));
+    const size_t smem = (size_t)K * 128 * sizeof(float2);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_F32)
+        target_apply_kernel<float><<<grid, 256, smem, st>>>(layers_dev, (const float2*)stats, y, K, B, T, D, rpb);
+    else
+        target_apply_kernel<bf16><<<grid, 256, smem, st>>>(layers_dev, (const float2*)stats, y, K, B, T, D, rpb);
+    return a2v_check_launch("target_apply");
+}
+
+extern "C" int a2v_d2v_loss_fwd(int dtype, const void* pred, const float* y, const uint8_t* mask, int64_t R, int T,
+                                int clones, int D, float scale, double* loss_sum, double* colstats,
+                                a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "d2v_loss_fwd: bad dtype");
+    A2V_REQUIRE(pred && y && mask && loss_sum && colstats && R >= 0 && T > 0 && clones >= 1 && D > 0 && D % 4 == 0,
+                "d2v_loss_fwd: bad arguments");
+    if (R == 0) return A2V_OK;
+    const long long RT = (long long)R * T;
+    const int cblocks = ceil_div(D, 128);
+    long long nblk = (long long)a2v_num_sms() * 8 / cblocks;
+    if (nblk < 1) nblk = 1;
+    if (nblk > ceil_div64(RT, 8)) nblk = ceil_div64(RT, 8);
+    const long long rpb = ceil_div64(RT, nblk);
+    dim3 grid(cblocks, (unsigned)ceil_div64(RT, rpb));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_F32)
+        d2v_loss_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)pred, y, mask, RT, T, clones, D, scale, rpb,
+                                                          loss_sum, colstats);
+    else
+        d2v_loss_fwd_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)pred, y, mask, RT, T, clones, D, scale, rpb,
+                                                         loss_sum, colstats);
+    return a2v_check_launch("d2v_loss_fwd");
+}
+
+extern "C" int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t* mask, void* dpred,
+                                int64_t R, int T, int clones, int D, float scale, const float* grad_out_dev,
+                                a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "d2v_loss_bwd: bad dtype");
+    A2V_REQUIRE(pred && y && mask && dpred && R >= 0 && T > 0 && clones >= 1 && D > 0 && D % 4 == 0,
+                "d2v_loss_bwd: bad arguments");
+    if (R == 0) return A2V_OK;
+    const long long RT = (long long)R * T;
+    long long blocks = ceil_div64(RT, 8);
+    const long long cap = (long long)a2v_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_F32)
+        d2v_loss_bwd_kernel<float><<<(int)blocks, 256, 0, st>>>((const float*)pred, y, mask, (float*)dpred, RT, T,
+                                                                 clones, D, 2.f * scale, grad_out_dev);
+    else
+        d2v_loss_bwd_kernel<bf16><<<(int)blocks, 256, 0, st>>>((const bf16*)pred, y, mask, (bf16*)dpred, RT, T, clones,
+                                                                D, 2.f * scale, grad_out_dev);
+    return a2v_check_launch("d2v_loss_bwd");
+}

@@ -1,0 +1,275 @@
+// SincNet band-pass front end (fp32 CUDA cores; the filters are regenerated every step).
+//
+// Reference behaviour replaced (file:line under /root/reference):
+//   nn/sinc.py:181-223  _get_sinc_filters  -> a2v_sinc_filters_fwd / _bwd
+//   nn/sinc.py:286-313  reflect "same" padding (31/31) and sinc.py:144-151 fp32 F.conv1d
+//                       -> a2v_sinc_conv_fwd (padding folded into the tile load, filters in smem)
+//   autograd of the conv w.r.t. the filters -> a2v_sinc_conv_wgrad
+// Output layout is channels-last (B, N, Cpad) with Cpad = 128 (channel 127 is a zero pad) so
+// that the next stage (LayerNorm over channels, then a K = 10*128 GEMM) reads contiguous rows.
+#include "common.cuh"
+#include "../../include/a2v_capi.h"
+
+namespace a2v {
+
+constexpr int SINC_CPAD = 128;
+constexpr int SINC_KMAX = 128;
+
+// one block (64 threads) per channel
+__global__ void sinc_filters_fwd_kernel(const float* __restrict__ low_hz, const float* __restrict__ band_hz,
+                                        const float* __restrict__ n_, const float* __restrict__ window_, int C, int K,
+                                        float min_low, float min_band, float nyquist, float* __restrict__ filt) {
+    const int c = blockIdx.x;
+    const int half = K / 2;
+    float* f = filt + (long long)c * K;
+    if (c >= C) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x) f[i] = 0.f;
+        return;
+    }
+    const float low = min_low + fabsf(low_hz[c]);
+    const float high = fminf(fmaxf(low + min_band + fabsf(band_hz[c]), min_low), nyquist);
+    const float band = high - low;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const float n = n_[i];
+        const float left = (sinf(high * n) - sinf(low * n)) / n * 2.f * window_[i];
+        const float v = left / (2.f * band);
+        f[i] = v;
+        f[K - 1 - i] = v;
+    }
+    if (threadIdx.x == 0) f[half] = (2.f * band) / (2.f * band);
+}
+
+__global__ void sinc_filters_bwd_kernel(const float* __restrict__ low_hz, const float* __restrict__ band_hz,
+                                        const float* __restrict__ n_, const float* __restrict__ window_, int C, int K,
+                                        float min_low, float min_band, float nyquist,
+                                        const float* __restrict__ dfilt, float* __restrict__ dlow,
+                                        float* __restrict__ dband) {
+    const int c = blockIdx.x;
+    if (c >= C) return;
+    const int half = K / 2;
+    const float lraw = low_hz[c], braw = band_hz[c];
+    const float low = min_low + fabsf(lraw);
+    const float pre = low + min_band + fabsf(braw);
+    const float high = fminf(fmaxf(pre, min_low), nyquist);
+    const bool unclamped = pre >= min_low && pre <= nyquist;
+    const float band = high - low;
+    const float* g = dfilt + (long long)c * K;
+    float d_high = 0.f, d_low = 0.f;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        const float n = n_[i], w = window_[i];
+        const float G = g[i] + g[K - 1 - i];
+        const float gi = (sinf(high * n) - sinf(low * n)) * w / n;  // filter_left * band
+        d_high += G * (cosf(high * n) * w / band - gi / (band * band));
+        d_low += G * (-cosf(low * n) * w / band + gi / (band * band));
+    }
+    d_high = warp_sum(d_high);
+    d_low = warp_sum(d_low);
+    __shared__ float sh[2][2];
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = d_high;
+        sh[1][threadIdx.x >> 5] = d_low;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float dh = sh[0][0] + sh[0][1], dl = sh[1][0] + sh[1][1];
+        const float sl = lraw > 0.f ? 1.f : (lraw < 0.f ? -1.f : 0.f);
+        const float sb = braw > 0.f ? 1.f : (braw < 0.f ? -1.f : 0.f);
+        const float dh_eff = unclamped ? dh : 0.f;
+        atomicAdd(dlow + c, (dl + dh_eff) * sl);
+        atomicAdd(dband + c, dh_eff * sb);
+    }
+}
+
+__device__ __forceinline__ int reflect_index(int j, int N) {
+    if (j < 0) j = -j;
+    if (j >= N) j = 2 * (N - 1) - j;
+    return j;
+}
+
+constexpr int SINC_TT = 128;  // time steps per tile
+
+// y[b, t, c] = sum_k filt[c][k] * x[b, reflect(t + k - K/2)]
+template <typename TO>
+__global__ void __launch_bounds__(256) sinc_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ filt,
+                                                            TO* __restrict__ y, int N, int K) {
+    extern __shared__ float sm[];
+    float* sf = sm;                      // [K][128]
+    float* sx = sm + K * SINC_CPAD;      // [SINC_TT + K - 1 + 3]
+    const int b = blockIdx.y, t0 = blockIdx.x * SINC_TT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < K * SINC_CPAD; i += 256) {
+        const int k = i / SINC_CPAD, c = i - k * SINC_CPAD;
+        sf[i] = filt[(long long)c * K + k];
+    }
+    const int half = K / 2;
+    const float* xb = x + (long long)b * N;
+    for (int i = threadIdx.x; i < SINC_TT + K + 2; i += 256) {
+        const int j = t0 + i - half;
+        sx[i] = (j < N + half) ? xb[reflect_index(j, N)] : 0.f;
+    }
+    __syncthreads();
+    // warp w: time steps w*16 .. w*16+15, 4 at a time; lane: channels lane*4 .. lane*4+3
+    for (int g = 0; g < 4; ++g) {
+        const int tl = warp * 16 + g * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+        float x0 = sx[tl], x1 = sx[tl + 1], x2 = sx[tl + 2];
+        for (int k = 0; k < K; ++k) {
+            const float x3 = sx[tl + k + 3];
+            const float4 f = *reinterpret_cast<const float4*>(sf + k * SINC_CPAD + lane * 4);
+            const float xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                acc[a][0] += xs[a] * f.x;
+                acc[a][1] += xs[a] * f.y;
+                acc[a][2] += xs[a] * f.z;
+                acc[a][3] += xs[a] * f.w;
+            }
+            x0 = x1; x1 = x2; x2 = x3;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int t = t0 + tl + a;
+            if (t < N) store4(y + ((long long)b * N + t) * SINC_CPAD + lane * 4, acc[a]);
+        }
+    }
+}
+
+// dfilt[c][k] += sum_{b,t} dy[b, t, c] * x[b, reflect(t + k - K/2)]
+// grid (chunks, B); each block walks its chunk of time steps in tiles of SINC_TT.
+template <typename TI>
+__global__ void __launch_bounds__(256) sinc_conv_wgrad_kernel(const float* __restrict__ x, const TI* __restrict__ dy,
+                                                              float* __restrict__ dfilt, int N, int K,
+                                                              int steps_per_block) {
+    extern __shared__ float sm[];
+    float* sdy = sm;                         // [SINC_TT][128]
+    float* sx = sm + SINC_TT * SINC_CPAD;    // [SINC_TT + K]
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = K / 2;
+    const int kpw = (K + 7) / 8;             // taps per warp (<= 16)
+    const int k_begin = warp * kpw;
+    float acc[16][4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[k][c] = 0.f;
+    const float* xb = x + (long long)b * N;
+    const int c_begin = blockIdx.x * steps_per_block;
+    const int c_end = min(N, c_begin + steps_per_block);
+    for (int t0 = c_begin; t0 < c_end; t0 += SINC_TT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SINC_TT * 32; i += 256) {
+            const int tl = i >> 5, c4 = (i & 31) * 4;
+            const int t = t0 + tl;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (t < c_end) load4(dy + ((long long)b * N + t) * SINC_CPAD + c4, v);
+            *reinterpret_cast<float4*>(sdy + tl * SINC_CPAD + c4) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        for (int i = threadIdx.x; i < SINC_TT + K; i += 256) {
+            const int j = t0 + i - half;
+            sx[i] = (j < N + half) ? xb[reflect_index(j, N)] : 0.f;
+        }
+        __syncthreads();
+        for (int tl = 0; tl < SINC_TT; ++tl) {
+            const float4 d = *reinterpret_cast<const float4*>(sdy + tl * SINC_CPAD + lane * 4);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                if (k < kpw && k_begin + k < K) {
+                    const float xv = sx[tl + k_begin + k];
+                    acc[k][0] += d.x * xv;
+                    acc[k][1] += d.y * xv;
+                    acc[k][2] += d.z * xv;
+                    acc[k][3] += d.w * xv;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < kpw && k_begin + k < K) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(dfilt + (long long)(lane * 4 + c) * K + k_begin + k, acc[k][c]);
+        }
+    }
+}
+
+}  // namespace a2v
+
+using namespace a2v;
+
+static int check_sinc_args(int C, int K) {
+    A2V_REQUIRE(C > 0 && C <= SINC_CPAD, "sinc: out_channels must be in (0, 128], got %d", C);
+    A2V_REQUIRE(K >= 3 && (K & 1) == 1 && K <= SINC_KMAX, "sinc: kernel_size must be odd and <= %d, got %d", SINC_KMAX, K);
+    return A2V_OK;
+}
+
+extern "C" int a2v_sinc_filters_fwd(const float* low_hz, const float* band_hz, const float* n_, const float* window_,
+                                    int C, int K, float min_low_hz, float min_band_hz, float sample_rate,
+                                    float* filters, a2v_stream_t stream) {
+    int rc = check_sinc_args(C, K);
+    if (rc != A2V_OK) return rc;
+    A2V_REQUIRE(low_hz && band_hz && n_ && window_ && filters, "sinc_filters_fwd: NULL pointer");
+    sinc_filters_fwd_kernel<<<SINC_CPAD, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        low_hz, band_hz, n_, window_, C, K, min_low_hz, min_band_hz, sample_rate * 0.5f, filters);
+    return a2v_check_launch("sinc_filters_fwd");
+}
+
+extern "C" int a2v_sinc_filters_bwd(const float* low_hz, const float* band_hz, const float* n_, const float* window_,
+                                    int C, int K, float min_low_hz, float min_band_hz, float sample_rate,
+                                    const float* dfilters, float* dlow_hz, float* dband_hz, a2v_stream_t stream) {
+    int rc = check_sinc_args(C, K);
+    if (rc != A2V_OK) return rc;
+    A2V_REQUIRE(low_hz && band_hz && n_ && window_ && dfilters && dlow_hz && dband_hz, "sinc_filters_bwd: NULL pointer");
+    sinc_filters_bwd_kernel<<<C, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        low_hz, band_hz, n_, window_, C, K, min_low_hz, min_band_hz, sample_rate * 0.5f, dfilters, dlow_hz, dband_hz);
+    return a2v_check_launch("sinc_filters_bwd");
+}
+
+extern "C" int a2v_sinc_conv_fwd(int out_dtype, const float* x, const float* filters, void* y, int B, int N, int K,
+                                 a2v_stream_t stream) {
+    int rc = check_sinc_args(1, K);
+    if (rc != A2V_OK) return rc;
+    A2V_REQUIRE(x && filters && y && B > 0 && N > K, "sinc_conv_fwd: bad arguments");
+    A2V_REQUIRE(out_dtype == A2V_F32 || out_dtype == A2V_BF16, "sinc_conv_fwd: bad dtype");
+    const size_t smem = (size_t)(K * SINC_CPAD + SINC_TT + K + 3) * sizeof(float);
+    dim3 grid(ceil_div(N, SINC_TT), B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (out_dtype == A2V_F32) {
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(sinc_conv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        sinc_conv_fwd_kernel<float><<<grid, 256, smem, st>>>(x, filters, (float*)y, N, K);
+    } else {
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(sinc_conv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        sinc_conv_fwd_kernel<bf16><<<grid, 256, smem, st>>>(x, filters, (bf16*)y, N, K);
+    }
+    return a2v_check_launch("sinc_conv_fwd");
+}
+
+extern "C" int a2v_sinc_conv_wgrad(int dy_dtype, const float* x, const void* dy, float* dfilters, int B, int N, int K,
+                                   a2v_stream_t stream) {
+    int rc = check_sinc_args(1, K);
+    if (rc != A2V_OK) return rc;
+    A2V_REQUIRE(x && dy && dfilters && B > 0 && N > K, "sinc_conv_wgrad: bad arguments");
+    A2V_REQUIRE(dy_dtype == A2V_F32 || dy_dtype == A2V_BF16, "sinc_conv_wgrad: bad dtype");
+    const size_t smem = (size_t)(SINC_TT * SINC_CPAD + SINC_TT + K) * sizeof(float);
+    int chunks = (a2v_num_sms() * 2) / B;
+    if (chunks < 1) chunks = 1;
+    int steps = ceil_div(ceil_div(N, chunks), SINC_TT) * SINC_TT;
+    dim3 grid(ceil_div(N, steps), B);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dy_dtype == A2V_F32) {
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(sinc_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        sinc_conv_wgrad_kernel<float><<<grid, 256, smem, st>>>(x, (const float*)dy, dfilters, N, K, steps);
+    } else {
+        static bool cfg = false;
+        if (!cfg) { cudaFuncSetAttribute(sinc_conv_wgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        sinc_conv_wgrad_kernel<bf16><<<grid, 256, smem, st>>>(x, (const bf16*)dy, dfilters, N, K, steps);
+    }
+    return a2v_check_launch("sinc_conv_wgrad");
+}

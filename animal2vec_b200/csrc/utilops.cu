@@ -1,0 +1,308 @@
+// Small HBM-bound utilities: column sums (bias gradients), strided cast/permute (weight
+// layouts for the GEMM), bf16 hi/lo splitting (validation "fp32 mode" of the GEMM),
+// fused EMA teacher update, fused AdamW, gradient norm / clip coefficient.
+//
+// Reference behaviour replaced:
+//   fairseq EMAModule.step + load_state_dict (called nn/data2vec2.py:408)  -> a2v_ema_step
+//   fairseq Adam (decoupled weight decay) + clip_grad_norm (yaml clip_norm) -> a2v_adamw_step,
+//   a2v_sumsq, a2v_clip_coef
+#include "common.cuh"
+#include "../../include/a2v_capi.h"
+
+namespace a2v {
+
+// ---------------------------------------------------------------- column sums
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows,
+                                                     int C, long long rows_per_block) {
+    __shared__ float part[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 128 + lane * 4;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c < C) {
+        for (long long r = r0 + warp; r < r1; r += 8) {
+            float v[4];
+            load4(x + r * C + c, v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) part[warp][lane * 4 + j] = acc[j];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+        const int cc = blockIdx.x * 128 + threadIdx.x;
+        if (cc < C) atomicAdd(out + cc, s);
+    }
+}
+
+// ---------------------------------------------------------------- strided cast / permute (4-D)
+struct PermuteParams {
+    const void* in;
+    void* out;
+    long long dims[4];
+    long long in_strides[4];
+    long long in_offset;
+    long long total;
+};
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_strided_kernel(const PermuteParams p) {
+    const TI* in = reinterpret_cast<const TI*>(p.in);
+    TO* out = reinterpret_cast<TO*>(p.out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long rem = i;
+        const long long i3 = rem % p.dims[3]; rem /= p.dims[3];
+        const long long i2 = rem % p.dims[2]; rem /= p.dims[2];
+        const long long i1 = rem % p.dims[1]; rem /= p.dims[1];
+        const long long i0 = rem;
+        const long long src = p.in_offset + i0 * p.in_strides[0] + i1 * p.in_strides[1] + i2 * p.in_strides[2] +
+                              i3 * p.in_strides[3];
+        out[i] = from_f32<TO>(src >= 0 ? to_f32(in[src]) : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------- flat elementwise
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                            long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float v[4];
+        load4(in + 4 * i, v);
+        store4(out + 4 * i, v);
+    }
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi); written K-concatenated per row as
+// pattern 0: [hi | hi | lo], pattern 1: [hi | lo | hi] so that an ordinary bf16 GEMM over 3K
+// computes hi*hi + hi*lo + lo*hi (about 16 mantissa bits) -- the validation "fp32 mode".
+// pattern 2/3: the same stacked along rows (for MN-major / reduction-over-rows products).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ in, bf16* __restrict__ out,
+                                                     long long rows, int K, int pattern) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows * K;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / K;
+        const int k = (int)(i - r * K);
+        const float x = in[i];
+        const bf16 hi = __float2bfloat16_rn(x);
+        const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+        const bf16 second = (pattern & 1) ? lo : hi;
+        const bf16 third = (pattern & 1) ? hi : lo;
+        if (pattern < 2) {
+            bf16* o = out + r * 3 * K;
+            o[k] = hi;
+            o[K + k] = second;
+            o[2 * K + k] = third;
+        } else {
+            out[i] = hi;
+            out[rows * K + i] = second;
+            out[2 * rows * K + i] = third;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- EMA teacher update
+// shadow = decay * shadow + (1 - decay) * student   (fp32 master of the teacher)
+// teacher_lp = bf16(shadow)                         (the copy the teacher GEMMs read)
+// 4 B read (student) + 4 B read + 4 B write (shadow) + 2 B write (bf16) per parameter.
+__global__ void __launch_bounds__(256) ema_kernel(const float* __restrict__ student, float* __restrict__ shadow,
+                                                  bf16* __restrict__ teacher_lp, long long n4, float decay) {
+    const float om = 1.0f - decay;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float s[4], e[4];
+        load4(student + 4 * i, s);
+        load4(shadow + 4 * i, e);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) e[j] = e[j] * decay + s[j] * om;  // mul_(decay).add_(p, alpha=1-decay)
+        store4(shadow + 4 * i, e);
+        if (teacher_lp != nullptr) store4(teacher_lp + 4 * i, e);
+    }
+}
+
+// ---------------------------------------------------------------- AdamW (fairseq Adam semantics)
+struct AdamParams {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    bf16* p_lp;
+    long long n4;
+    float lr, beta1, beta2, eps, wd, step_size;
+    const float* grad_scale;  // device scalar multiplied into every gradient (clip * 1/sample_size), may be NULL
+};
+
+__global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
+    const float gs = a.grad_scale != nullptr ? *a.grad_scale : 1.0f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n4; i += (long long)gridDim.x * blockDim.x) {
+        float p[4], g[4], m[4], v[4];
+        load4(a.p + 4 * i, p);
+        load4(a.g + 4 * i, g);
+        load4(a.m + 4 * i, m);
+        load4(a.v + 4 * i, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gj = g[j] * gs;
+            m[j] = a.beta1 * m[j] + (1.f - a.beta1) * gj;
+            v[j] = a.beta2 * v[j] + (1.f - a.beta2) * gj * gj;
+            const float denom = sqrtf(v[j]) + a.eps;
+            p[j] = p[j] - a.lr * a.wd * p[j];      // decoupled weight decay: p.add_(p, alpha=-wd*lr)
+            p[j] = p[j] - a.step_size * m[j] / denom;
+        }
+        store4(a.p + 4 * i, p);
+        store4(a.m + 4 * i, m);
+        store4(a.v + 4 * i, v);
+        if (a.p_lp != nullptr) store4(a.p_lp + 4 * i, p);
+    }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+    __shared__ float wsum[8];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = x[i];
+        acc += v * v;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int w = 0; w < 8; ++w) s += wsum[w];
+        atomicAdd(out, (double)s);
+    }
+}
+
+// out[0] = grad_mult * min(1, max_norm / (grad_mult * sqrt(sumsq) + 1e-6)), out[1] = grad_mult * sqrt(sumsq)
+// grad_mult = numer / denom[0] (e.g. world_size / sample_size) when denom is given.
+__global__ void clip_coef_kernel(const double* __restrict__ sumsq, const float* __restrict__ denom, float numer,
+                                 float max_norm, float* __restrict__ out) {
+    float mult = numer;
+    if (denom != nullptr) mult = numer / fmaxf(*denom, 1e-20f);
+    const float norm = mult * (float)sqrt(*sumsq);
+    float coef = 1.f;
+    if (max_norm > 0.f) coef = fminf(1.f, max_norm / (norm + 1e-6f));
+    out[0] = mult * coef;
+    out[1] = norm;
+}
+
+static int flat_grid(long long n) {
+    long long b = ceil_div64(n, 256);
+    long long cap = (long long)a2v_num_sms() * 8;
+    if (b > cap) b = cap;
+    return b < 1 ? 1 : (int)b;
+}
+
+}  // namespace a2v
+
+using namespace a2v;
+
+extern "C" int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "colsum: bad dtype");
+    A2V_REQUIRE(x && out && C > 0 && C % 4 == 0 && rows >= 0, "colsum: bad arguments");
+    if (rows == 0) return A2V_OK;
+    const int cblocks = ceil_div(C, 128);
+    int rblocks = (int)((long long)a2v_num_sms() * 4 / cblocks);
+    if (rblocks < 1) rblocks = 1;
+    if (rblocks > rows / 8 + 1) rblocks = (int)(rows / 8 + 1);
+    const long long rpb = ceil_div64(rows, rblocks);
+    dim3 grid(cblocks, rblocks);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_F32)
+        colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, rows, C, rpb);
+    else
+        colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, out, rows, C, rpb);
+    return a2v_check_launch("colsum");
+}
+
+extern "C" int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
+                                const int64_t* in_strides4, int64_t in_offset, a2v_stream_t stream) {
+    A2V_REQUIRE(in && out && dims4 && in_strides4, "cast_strided: NULL pointer");
+    PermuteParams p;
+    p.in = in;
+    p.out = out;
+    p.total = 1;
+    for (int i = 0; i < 4; ++i) {
+        A2V_REQUIRE(dims4[i] > 0, "cast_strided: dims must be positive");
+        p.dims[i] = dims4[i];
+        p.in_strides[i] = in_strides4[i];
+        p.total *= dims4[i];
+    }
+    p.in_offset = in_offset;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = flat_grid(p.total);
+    if (in_dtype == A2V_F32 && out_dtype == A2V_BF16)
+        cast_strided_kernel<float, bf16><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_F32 && out_dtype == A2V_F32)
+        cast_strided_kernel<float, float><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_BF16 && out_dtype == A2V_BF16)
+        cast_strided_kernel<bf16, bf16><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_BF16 && out_dtype == A2V_F32)
+        cast_strided_kernel<bf16, float><<<grid, 256, 0, st>>>(p);
+    else {
+        a2v_set_error("cast_strided: bad dtypes");
+        return A2V_ERR_ARG;
+    }
+    return a2v_check_launch("cast_strided");
+}
+
+extern "C" int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream) {
+    A2V_REQUIRE(in && out && n >= 0 && n % 4 == 0, "cast_f32_to_bf16: n must be a multiple of 4");
+    if (n == 0) return A2V_OK;
+    cast_f32_bf16_kernel<<<flat_grid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n / 4);
+    return a2v_check_launch("cast_f32_to_bf16");
+}
+
+extern "C" int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream) {
+    A2V_REQUIRE(in && out && rows >= 0 && K > 0 && pattern >= 0 && pattern <= 3, "split3: bad arguments");
+    if (rows == 0) return A2V_OK;
+    split3_kernel<<<flat_grid(rows * K), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, rows, K,
+                                                                                          pattern);
+    return a2v_check_launch("split3");
+}
+
+extern "C" int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_t n, float decay,
+                            a2v_stream_t stream) {
+    A2V_REQUIRE(student && shadow && n >= 0 && n % 4 == 0, "ema_step: n must be a multiple of 4");
+    A2V_REQUIRE(((uintptr_t)student & 15) == 0 && ((uintptr_t)shadow & 15) == 0 && ((uintptr_t)teacher_bf16 & 7) == 0,
+                "ema_step: buffers must be 16-byte aligned");
+    if (n == 0) return A2V_OK;
+    ema_kernel<<<flat_grid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(student, shadow,
+                                                                                     (bf16*)teacher_bf16, n / 4, decay);
+    return a2v_check_launch("ema_step");
+}
+
+extern "C" int a2v_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
+                              float beta1, float beta2, float eps, float weight_decay, int step,
+                              const float* grad_scale, a2v_stream_t stream) {
+    A2V_REQUIRE(p && g && m && v && n >= 0 && n % 4 == 0 && step >= 1, "adamw_step: bad arguments");
+    if (n == 0) return A2V_OK;
+    AdamParams a;
+    a.p = p; a.g = g; a.m = m; a.v = v; a.p_lp = (bf16*)p_bf16; a.n4 = n / 4;
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    a.step_size = (float)((double)lr * sqrt(bc2) / bc1);
+    a.grad_scale = grad_scale;
+    adamw_kernel<<<flat_grid(a.n4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    return a2v_check_launch("adamw_step");
+}
+
+extern "C" int a2v_sumsq(const float* x, int64_t n, double* out, a2v_stream_t stream) {
+    A2V_REQUIRE(x && out && n >= 0, "sumsq: bad arguments");
+    if (n == 0) return A2V_OK;
+    sumsq_kernel<<<flat_grid(n), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, n, out);
+    return a2v_check_launch("sumsq");
+}
+
+extern "C" int a2v_clip_coef(const double* sumsq, const float* denom, float numer, float max_norm, float* out2,
+                             a2v_stream_t stream) {
+    A2V_REQUIRE(sumsq && out2, "clip_coef: NULL pointer");
+    clip_coef_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sumsq, denom, numer, max_norm, out2);
+    return a2v_check_launch("clip_coef");
+}

@@ -98,6 +98,196 @@ typedef struct {
 
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Fused row LayerNorm family (HBM-bound, warp-per-row):
+ *   z = a + dropout_b(b);  n = LN(z) * gamma + beta;  y = dropout_out(act(n)) + post
+ * Replaces: Fp32LayerNorm+PSwish / +GELU of the feature extractor (nn/utils.py:1105-1117,
+ * 1413-1435), project_features' Fp32LayerNorm (nn/modalities/audio.py:86), LayerNorm+GELU
+ * of the positional-conv and decoder stacks (audio.py:104-108, nn/modalities/modules.py:
+ * 150-157, residual 124-134), AltBlock's post-LN residual norms (modules.py:329-333) and
+ * BlockEncoder's LN -> dropout (modules.py:84-87).
+ * channels-last rows of `channels` stored elements; a "group-padded" layout has
+ * `group_real` meaningful channels in every `group_width` stored ones (pads are kept 0;
+ * gamma/beta/act parameters are indexed by the real channel index).
+ * act: 0 none, 1 exact GELU, 2 PSwish (n * alpha_c * sigmoid(beta_c * n)).
+ * Dropout masks come from a counter-based hash of (seed, element index) and are
+ * regenerated by the backward pass, never stored.
+ * Backward: da = dL/dz, db = dropout_b-masked da, parameter gradients are atomically
+ * accumulated (fp32) into dgamma/dbeta/dact_alpha/dact_beta when non-NULL. `mean`/`rstd`
+ * (fp32 per row) are written by the forward and read by the backward.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int dtype;                 /* of a, b, post, y, dy, da, db */
+    int64_t rows;
+    int channels, group_width, group_real;
+    float eps;
+    int act;
+    const void* a;
+    const void* b;             /* optional */
+    const float* gamma;        /* optional */
+    const float* beta;         /* optional */
+    const float* act_alpha;    /* PSwish */
+    const float* act_beta;
+    const void* post;          /* optional, added after the activation */
+    void* y;
+    float* mean;
+    float* rstd;
+    float drop_b;
+    uint64_t seed_b;
+    float drop_out;
+    uint64_t seed_out;
+    /* backward only */
+    const void* dy;
+    void* da;
+    void* db;
+    float* dgamma;
+    float* dbeta;
+    float* dact_alpha;
+    float* dact_beta;
+} a2v_rowln_desc;
+
+int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream);
+int a2v_rowln_bwd(const a2v_rowln_desc* d, a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Masking and multi-mask cloning (HBM-bound data movement).
+ *  a2v_mask_index: from the uint8 mask (rows = B*clones, 1 = masked) build
+ *    ids_keep [rows,Tk], ids_restore [rows,T] (MaskInfo of nn/modalities/base.py:427-455;
+ *    kept positions in ascending order) and the flat int32 row maps the gathers use:
+ *      clone_src[r*T+t]       = (r/clones)*T+t if kept else -1   (clone + zero mask, base.py:244,464)
+ *      keep_src_x[r*Tk+k]     = (r/clones)*T+ids_keep             (x_unmasked gather from the un-cloned x)
+ *      keep_src_clone[r*Tk+k] = r*T+ids_keep                      (gather_unmasked, base.py:537-542)
+ *      restore_src[r*T+t]     = r*Tk+rank if kept else -1         (decoder_input scatter, base.py:178-179)
+ *    err_flag is set to 1+row if a row does not keep exactly Tk positions.
+ *  a2v_row_gather: dst[o,:] = (idx[o] >= 0 ? dropout(src[idx[o],:]) : N(0, fill_std) or 0) + add[o,:].
+ *  a2v_clone_sum_bwd: gradient of clone+mask+gather summed over the clones of each clip.
+ * ------------------------------------------------------------------------------------ */
+int a2v_mask_index(const uint8_t* mask, int rows, int T, int Tk, int clones, int32_t* ids_keep,
+                   int32_t* ids_restore, int32_t* clone_src, int32_t* keep_src_x, int32_t* keep_src_clone,
+                   int32_t* restore_src, int32_t* err_flag, a2v_stream_t stream);
+int a2v_row_gather(int dtype, const void* src, const int32_t* idx, const void* add, void* dst, int64_t n_dst,
+                   int D, float fill_std, uint64_t fill_seed, float drop_p, uint64_t drop_seed, int drop_by_src,
+                   a2v_stream_t stream);
+int a2v_clone_sum_bwd(int dtype, const void* d_masked, const void* d_unmasked, const int32_t* restore_src,
+                      void* dx, int64_t B, int T, int clones, int D, a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Teacher targets and masked regression loss (HBM-bound).
+ *  a2v_target_stats / a2v_target_apply: nn/data2vec2.py:1023-1066 (instance-norm over time of
+ *    the top-K teacher FFN outputs, averaged). layers_dev = device array of K pointers to
+ *    (B,T,D) tensors; stats = (K,B,D,2) fp32 (mean, rstd); y = (B,T,D) fp32.
+ *  a2v_d2v_loss_fwd: data2vec2.py:850-862,1005-1021 + compute_var 1095-1110. pred (R,T,D) with
+ *    R = B*clones, y (B,T,D) fp32, mask (R,T) uint8. Adds scale*sum((pred-y)^2 over masked
+ *    rows) into loss_sum[0] (double) and the column sums [sum x, sum x^2, sum y, sum y^2]
+ *    over masked rows into colstats (4,D) doubles. Both must be zeroed by the caller.
+ *  a2v_d2v_loss_bwd: dpred = mask ? 2*scale*g*(pred-y) : 0, g = *grad_out_dev (or 1 if NULL).
+ * ------------------------------------------------------------------------------------ */
+int a2v_target_stats(int dtype, const void* const* layers_dev, int K, int B, int T, int D, float eps, float* stats,
+                     a2v_stream_t stream);
+int a2v_target_apply(int dtype, const void* const* layers_dev, int K, int B, int T, int D, const float* stats,
+                     float* y, a2v_stream_t stream);
+int a2v_d2v_loss_fwd(int dtype, const void* pred, const float* y, const uint8_t* mask, int64_t R, int T, int clones,
+                     int D, float scale, double* loss_sum, double* colstats, a2v_stream_t stream);
+int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t* mask, void* dpred, int64_t R, int T,
+                     int clones, int D, float scale, const float* grad_out_dev, a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Utilities.
+ *  a2v_colsum: out[c] += sum_rows x[r,c] (bias gradients).
+ *  a2v_cast_strided: dense 4-D out[i0,i1,i2,i3] = in[in_offset + sum i_d*in_strides[d]] with
+ *    dtype conversion (weight re-layouts: (O,I,k) -> (O,k,I), flips, transposes).
+ *  a2v_split3: bf16 hi/lo split for the validation-precision GEMM (see utilops.cu).
+ *  a2v_ema_step: fused EMA teacher update replacing fairseq EMAModule.step + reload
+ *    (called from nn/data2vec2.py:408): shadow = d*shadow + (1-d)*student, bf16 copy out.
+ *  a2v_adamw_step: fairseq Adam with decoupled weight decay; grads are multiplied by the
+ *    device scalar *grad_scale (clip coefficient x 1/sample_size); writes the bf16 copy.
+ *  a2v_sumsq / a2v_clip_coef: gradient-norm clipping without a host round trip.
+ * ------------------------------------------------------------------------------------ */
+int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream);
+int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
+                     const int64_t* in_strides4, int64_t in_offset, a2v_stream_t stream);
+int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream);
+int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream);
+int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_t n, float decay,
+                 a2v_stream_t stream);
+int a2v_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, const float* grad_scale,
+                   a2v_stream_t stream);
+int a2v_sumsq(const float* x, int64_t n, double* out, a2v_stream_t stream);
+int a2v_clip_coef(const double* sumsq, const float* denom, float numer, float max_norm, float* out2,
+                  a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Self-attention with on-the-fly ALiBi (replaces AltAttention.forward,
+ * nn/modalities/modules.py:368-410, and the whole bias-tensor machinery of
+ * nn/modalities/base.py:293-314,553-698).
+ *   qkv  : (batch, L, 3*H*64) rows [q | k | v], each (H, 64)   (output of the qkv Linear)
+ *   out  : (batch, L, H*64);  lse : (batch, H, L) fp32 log-sum-exp (needed by the backward)
+ *   pos  : (batch, L) int32 absolute token positions (ids_keep) or NULL for 0..L-1
+ *   bias[h,i,j] = -slopes[h] * max(alibi_scale[h*stride], 0) * |pos_i - pos_j|
+ *   dropout on the attention probabilities uses a counter-based hash of (seed, b, h, i, j).
+ * bf16: tcgen05/TMA flash-style forward; backward keeps one head resident in shared memory
+ * (L <= 160, the student's kept-token count). fp32: CUDA-core validation kernels; the fp32
+ * backward accumulates dK/dV atomically, so dqkv must be zeroed by the caller.
+ * dalibi_scale[h*stride] is atomically accumulated.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int dtype;
+    int batch, L, H, head_dim;
+    const void* qkv;
+    void* out;
+    float* lse;
+    const int32_t* pos;
+    const float* slopes;
+    const float* alibi_scale;
+    int alibi_scale_stride;
+    float sm_scale;
+    float drop_p;
+    uint64_t seed;
+    /* backward only */
+    const void* dout;
+    void* dqkv;
+    float* dalibi_scale;
+} a2v_attn_desc;
+
+int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream);
+int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * SincNet front end (nn/sinc.py:107-223,286-337). Channels-last output (B, N, 128) with the
+ * 127 band-pass channels in columns 0..126 and a zero pad column. filters / dfilters are
+ * (128, K) fp32 (row 127 zero). n_ and window_ are the (K/2,) fp32 buffers SincConv builds
+ * at construction (sinc.py:264-276). Only stride 1 / dilation 1 / reflect "same" padding.
+ * ------------------------------------------------------------------------------------ */
+int a2v_sinc_filters_fwd(const float* low_hz, const float* band_hz, const float* n_, const float* window_, int C,
+                         int K, float min_low_hz, float min_band_hz, float sample_rate, float* filters,
+                         a2v_stream_t stream);
+int a2v_sinc_filters_bwd(const float* low_hz, const float* band_hz, const float* n_, const float* window_, int C,
+                         int K, float min_low_hz, float min_band_hz, float sample_rate, const float* dfilters,
+                         float* dlow_hz, float* dband_hz, a2v_stream_t stream);
+int a2v_sinc_conv_fwd(int out_dtype, const float* x, const float* filters, void* y, int B, int N, int K,
+                      a2v_stream_t stream);
+int a2v_sinc_conv_wgrad(int dy_dtype, const float* x, const void* dy, float* dfilters, int B, int N, int K,
+                        a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Channels-last im2col / col2im for the strided feature-extractor convs (nn/utils.py:1085-1090).
+ * ------------------------------------------------------------------------------------ */
+int a2v_im2col(int dtype, const void* x, void* col, int B, int Tin, int Tout, int C, int k, int stride, int pad,
+               a2v_stream_t stream);
+int a2v_col2im(int dtype, const void* dcol, void* dx, int B, int Tin, int Tout, int C, int k, int stride, int pad,
+               a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * BC-learning mixup (nn/data2vec2.py:453-498,536-598). gain_db is (B, W), W = (N-n_fft)/hop+1.
+ * aweight = 10^(A-weighting dB / 10) for the n_fft/2+1 rfft bins (the reference builds it in
+ * float64, data2vec2.py:461-479; pass it rounded to fp32). p_out (B,) optionally receives p.
+ * ------------------------------------------------------------------------------------ */
+int a2v_mixup_gain(const float* x, const float* hann, const float* aweight, int B, int N, int n_fft, int hop,
+                   float min_db, float* gain_db, a2v_stream_t stream);
+int a2v_mixup_apply(const float* x, const int32_t* perm, const float* gain_db, int B, int N, int W, float r,
+                    float* out, float* p_out, a2v_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

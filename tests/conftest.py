@@ -27,3 +27,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_torch_references():
+    """torch's own conv/matmul default to TF32 on sm_100; the references must be true fp32."""
+    try:
+        import torch
+
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:
+        pass
+    yield
