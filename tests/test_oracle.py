@@ -1,0 +1,122 @@
+"""CPU tests: the oracle restatement (oracle/a2v_oracle.py) against golden vectors produced by
+running the real reference code (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import a2v_oracle as O
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name), allow_pickle=False))
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _sub(t, rows=7, cols=5):
+    t = t.detach().float()
+    return t[:, ::rows, ::cols] if t.dim() == 3 else t
+
+
+def _inputs(g):
+    b, n = int(g["b"]), int(g["n"])
+    gen = torch.Generator().manual_seed(int(g["seed_x"]))
+    x = F.layer_norm(torch.randn(b, n, generator=gen), (n,))
+    return x, torch.arange(b)
+
+
+@pytest.mark.parametrize("name,mixup", [("tiny_u0.npz", False), ("tiny_u7_mixup.npz", True)])
+def test_oracle_matches_reference_golden(name, mixup):
+    g = _load(name)
+    cfg = O.tiny_config()
+    student = O.init_params(cfg, int(g["seed_w"]))
+    teacher = O.make_teacher(student)
+    x, ids = _inputs(g)
+    taps = {}
+    for v in student.values():
+        v.requires_grad_(True)
+    torch.manual_seed(int(g["torch_seed"]))
+    res = O.pretrain_forward(student, teacher, cfg, x, ids, int(g["num_updates"]), do_mixup=mixup, taps=taps)
+
+    # integer work: bit exact
+    mask = np.unpackbits(g["mask_packed"], axis=1)[:, : int(g["T"])].astype(bool)
+    assert np.array_equal(res["mask"].numpy(), mask)
+    assert int(res["sample_size"]) == int(g["sample_size"])
+    assert abs(res["masked_pct"] - float(g["masked_pct"])) < 1e-12
+
+    # floating point stages: 1e-4 relative (fp32 CPU vs fp32 CPU, different op order)
+    tol = 1e-4
+    if mixup:
+        assert _rel(taps["mixed_source"][:, ::37], g["mixed_source"]) < tol
+    for i in range(8):
+        t = taps[f"fe_layer{i}"].transpose(1, 2)
+        got = t.detach()[:, :: max(1, t.shape[1] // 50), ::3]
+        assert _rel(got, g[f"fe_layer{i}"]) < tol, i
+    for k in ("local_features", "student_prenet", "student_out", "decoder_out", "targets"):
+        assert _rel(_sub(taps[k]), g[k]) < tol, (k, _rel(_sub(taps[k]), g[k]))
+    loss = res["losses"]["AUDIO_regression"].sum()
+    assert abs(loss.item() - float(g["loss_sum"])) / float(g["loss_sum"]) < tol
+    assert abs(float(res["pred_var"]) - float(g["pred_var"])) / float(g["pred_var"]) < tol
+    assert abs(float(res["target_var"]) - float(g["target_var"])) / float(g["target_var"]) < tol
+
+    # gradients
+    loss.backward()
+    keys = [str(k) for k in g["grad_keys"]]
+    assert set(keys) == set(k for k, v in student.items() if v.grad is not None)
+    for k, nrm, head in zip(keys, g["grad_norms"], g["grad_heads"]):
+        gr = student[k].grad
+        assert abs(gr.norm().item() - nrm) <= 2e-3 * nrm + 1e-7, (k, gr.norm().item(), nrm)
+        h = gr.flatten()[:8]
+        assert np.allclose(h.numpy(), head[: h.numel()], rtol=5e-3, atol=2e-3 * (nrm / max(1.0, gr.numel() ** 0.5)) + 1e-7), k
+
+    # EMA step
+    decay = O.annealed_decay(cfg, int(g["num_updates"]) + 1)
+    assert abs(decay - float(g["ema_decay_after"])) < 1e-12
+    with torch.no_grad():
+        O.ema_step(student, teacher, decay)
+    ek = [str(k) for k in g["ema_keys"]]
+    assert set(ek) == set(teacher.keys())
+    for k, s, sa in zip(ek, g["ema_sums"], g["ema_abs_sums"]):
+        assert abs(float(teacher[k].double().sum()) - s) <= 1e-6 * sa + 1e-9, k
+
+
+def test_masks_large_bit_exact():
+    g = _load("masks_large.npz")
+    m, t, seed, nb = [int(v) for v in g["meta"]]
+    cfg = O.large_config(clone_batch=m, seed=seed)
+    ids = torch.as_tensor(g["ids"])
+    for u in g["updates"]:
+        ref = np.unpackbits(g[f"mask_u{int(u)}"], axis=1)[:, :t].astype(bool)
+        got = O.pretrain_mask(cfg, nb, t, ids, int(u))
+        assert np.array_equal(got, ref)
+        # documented expectations of the shipped recipe (yaml:129): ~93 % masked, equal count per row
+        assert len(set(got.sum(1).tolist())) == 1
+        assert 0.92 < got.mean() < 0.94
+
+
+def test_hash_probes_and_slopes():
+    # SURVEY.md Appendix A [probe] values (Python 3.12 tuple hashing)
+    assert int(hash((1, 7, 0)) % 1e6) == 697984
+    assert [int(hash((1, i)) % 1e10) for i in range(3)] == [7385056256, 2121911296, 4514358272]
+    assert np.allclose(O.alibi_slopes(16), [2 ** (-0.5 * (h + 1)) for h in range(16)])
+    s12 = O.alibi_slopes(12)
+    assert np.allclose(s12[:8], [2.0 ** -(i + 1) for i in range(8)])
+    assert np.allclose(s12[8:], [2 ** -0.5, 2 ** -1.5, 2 ** -2.5, 2 ** -3.5])
+
+
+def test_param_inventory_counts():
+    # SURVEY.md Appendix A [probe]: large student 315 830 026 params, teacher 308 542 480
+    shapes = O.student_param_shapes(O.large_config())
+    total = sum(int(np.prod(s)) for s in shapes.values())
+    teacher = sum(int(np.prod(s)) for k, s in shapes.items() if O.is_teacher_key(k))
+    assert total == 315_830_026
+    assert teacher == 308_542_480
