@@ -69,6 +69,42 @@ __global__ void __launch_bounds__(256) cast_strided_kernel(const PermuteParams p
     }
 }
 
+// ---------------------------------------------------------------- general 4-D re-layout
+// out[out_offset + sum i_d*out_strides[d]] (+)= in[in_offset + sum i_d*in_strides[d]]
+// (weight packing into padded / tap-major / transposed GEMM layouts and the inverse for
+// the weight gradients; destinations with pad slots are zero-initialised once by the caller)
+struct RelayoutParams {
+    const void* in;
+    void* out;
+    long long dims[4];
+    long long in_strides[4];
+    long long out_strides[4];
+    long long in_offset, out_offset;
+    long long total;
+    int accumulate;
+};
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) relayout_kernel(const RelayoutParams p) {
+    const TI* in = reinterpret_cast<const TI*>(p.in);
+    TO* out = reinterpret_cast<TO*>(p.out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long rem = i;
+        const long long i3 = rem % p.dims[3]; rem /= p.dims[3];
+        const long long i2 = rem % p.dims[2]; rem /= p.dims[2];
+        const long long i1 = rem % p.dims[1]; rem /= p.dims[1];
+        const long long i0 = rem;
+        const long long src = p.in_offset + i0 * p.in_strides[0] + i1 * p.in_strides[1] + i2 * p.in_strides[2] +
+                              i3 * p.in_strides[3];
+        const long long dst = p.out_offset + i0 * p.out_strides[0] + i1 * p.out_strides[1] + i2 * p.out_strides[2] +
+                              i3 * p.out_strides[3];
+        float v = to_f32(in[src]);
+        if (p.accumulate) v += to_f32(out[dst]);
+        out[dst] = from_f32<TO>(v);
+    }
+}
+
 // ---------------------------------------------------------------- flat elementwise
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                                             long long n4) {
@@ -249,6 +285,41 @@ extern "C" int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, voi
         return A2V_ERR_ARG;
     }
     return a2v_check_launch("cast_strided");
+}
+
+extern "C" int a2v_relayout(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
+                            const int64_t* in_strides4, int64_t in_offset, const int64_t* out_strides4,
+                            int64_t out_offset, int accumulate, a2v_stream_t stream) {
+    A2V_REQUIRE(in && out && dims4 && in_strides4 && out_strides4, "relayout: NULL pointer");
+    RelayoutParams p;
+    p.in = in;
+    p.out = out;
+    p.total = 1;
+    for (int i = 0; i < 4; ++i) {
+        A2V_REQUIRE(dims4[i] > 0, "relayout: dims must be positive");
+        p.dims[i] = dims4[i];
+        p.in_strides[i] = in_strides4[i];
+        p.out_strides[i] = out_strides4[i];
+        p.total *= dims4[i];
+    }
+    p.in_offset = in_offset;
+    p.out_offset = out_offset;
+    p.accumulate = accumulate;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = flat_grid(p.total);
+    if (in_dtype == A2V_F32 && out_dtype == A2V_BF16)
+        relayout_kernel<float, bf16><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_F32 && out_dtype == A2V_F32)
+        relayout_kernel<float, float><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_BF16 && out_dtype == A2V_BF16)
+        relayout_kernel<bf16, bf16><<<grid, 256, 0, st>>>(p);
+    else if (in_dtype == A2V_BF16 && out_dtype == A2V_F32)
+        relayout_kernel<bf16, float><<<grid, 256, 0, st>>>(p);
+    else {
+        a2v_set_error("relayout: bad dtypes");
+        return A2V_ERR_ARG;
+    }
+    return a2v_check_launch("relayout");
 }
 
 extern "C" int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream) {

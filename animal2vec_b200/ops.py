@@ -278,6 +278,22 @@ def cast_strided(src: torch.Tensor, dims, strides, offset=0, out_dtype=torch.bfl
     return out
 
 
+def relayout(src: torch.Tensor, dst: torch.Tensor, dims, in_strides, in_off, out_strides, out_off,
+             accumulate: bool = False) -> torch.Tensor:
+    """dst.flat[out_off + i.out_strides] (+)= src.flat[in_off + i.in_strides] over a <= 4-D index space."""
+    dims, in_strides, out_strides = list(dims), list(in_strides), list(out_strides)
+    while len(dims) < 4:
+        dims.insert(0, 1)
+        in_strides.insert(0, 0)
+        out_strides.insert(0, 0)
+    dd = (C.c_int64 * 4)(*dims)
+    si = (C.c_int64 * 4)(*in_strides)
+    so = (C.c_int64 * 4)(*out_strides)
+    _call("a2v_relayout", src, L.dtype_code(src), L.dtype_code(dst), _p(src), _p(dst), dd, si, C.c_int64(in_off), so,
+          C.c_int64(out_off), int(accumulate))
+    return dst
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert src.dtype == torch.float32 and src.is_contiguous() and src.numel() % 4 == 0
     if out is None:

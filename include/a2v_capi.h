@@ -206,6 +206,13 @@ int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t*
 int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream);
 int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
                      const int64_t* in_strides4, int64_t in_offset, a2v_stream_t stream);
+/* general 4-D re-layout with cast: out[out_offset + i.out_strides] (+)= in[in_offset + i.in_strides]
+ * (weight packing into tap-major / group-padded / transposed GEMM layouts and back for the
+ * weight gradients; the reference keeps torch's (out, in/groups, k) Conv1d layout,
+ * nn/modalities/audio.py:97-103, modules.py:143-149, nn/utils.py:1085-1090). */
+int a2v_relayout(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
+                 const int64_t* in_strides4, int64_t in_offset, const int64_t* out_strides4, int64_t out_offset,
+                 int accumulate, a2v_stream_t stream);
 int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream);
 int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream);
 int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_t n, float decay,
