@@ -171,6 +171,7 @@ struct AdamParams {
     long long n4;
     float lr, beta1, beta2, eps, wd, step_size;
     const float* grad_scale;  // device scalar multiplied into every gradient (clip * 1/sample_size), may be NULL
+    const uint8_t* wd_mask;   // per 4-element chunk: 0 = the weight_decay_scale-0 group (data2vec2.py:318-322), may be NULL
 };
 
 __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
@@ -181,13 +182,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
         load4(a.g + 4 * i, g);
         load4(a.m + 4 * i, m);
         load4(a.v + 4 * i, v);
+        const float wd = (a.wd_mask == nullptr || a.wd_mask[i] != 0) ? a.wd : 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float gj = g[j] * gs;
             m[j] = a.beta1 * m[j] + (1.f - a.beta1) * gj;
             v[j] = a.beta2 * v[j] + (1.f - a.beta2) * gj * gj;
             const float denom = sqrtf(v[j]) + a.eps;
-            p[j] = p[j] - a.lr * a.wd * p[j];      // decoupled weight decay: p.add_(p, alpha=-wd*lr)
+            p[j] = p[j] - a.lr * wd * p[j];      // decoupled weight decay: p.add_(p, alpha=-wd*lr)
             p[j] = p[j] - a.step_size * m[j] / denom;
         }
         store4(a.p + 4 * i, p);
@@ -350,7 +352,7 @@ extern "C" int a2v_ema_step(const float* student, float* shadow, void* teacher_b
 
 extern "C" int a2v_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr,
                               float beta1, float beta2, float eps, float weight_decay, int step,
-                              const float* grad_scale, a2v_stream_t stream) {
+                              const float* grad_scale, const uint8_t* wd_mask, a2v_stream_t stream) {
     A2V_REQUIRE(p && g && m && v && n >= 0 && n % 4 == 0 && step >= 1, "adamw_step: bad arguments");
     if (n == 0) return A2V_OK;
     AdamParams a;
@@ -360,6 +362,7 @@ extern "C" int a2v_adamw_step(float* p, const float* g, float* m, float* v, void
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     a.step_size = (float)((double)lr * sqrt(bc2) / bc1);
     a.grad_scale = grad_scale;
+    a.wd_mask = wd_mask;
     adamw_kernel<<<flat_grid(a.n4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     return a2v_check_launch("adamw_step");
 }

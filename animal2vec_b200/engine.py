@@ -175,6 +175,7 @@ class PretrainEngine:
                 raise KeyError(f"missing parameter {k}")
             self.S.view(k).copy_(tensors[k].to(self.device, torch.float32).reshape(self.S.shapes[k]))
         self._student_dirty = True
+        self._s16_valid = False
 
     def reset_teacher(self) -> None:
         """make_ema_teacher (nn/data2vec2.py:345-384): fp32 copy of the shared student parameters."""
@@ -188,8 +189,11 @@ class PretrainEngine:
         self._teacher_dirty = True
         self._t16_valid = False
 
-    def mark_student_updated(self) -> None:
+    def mark_student_updated(self, s16_valid: bool = False) -> None:
+        """The fp32 masters changed (optimizer step / state-dict load). ``s16_valid``: the bf16 flat copy was
+        already refreshed by the writer (the fused AdamW kernel stores it)."""
         self._student_dirty = True
+        self._s16_valid = s16_valid
 
     def _lin_names(self, prefix_list: Sequence[str]) -> List[str]:
         out = []
@@ -257,8 +261,9 @@ class PretrainEngine:
         if not self._student_dirty:
             return
         S, W = self.S, self.WS
-        if not self.fp32:
+        if not self.fp32 and not self._s16_valid:
             ops.cast_bf16(S.data, out=self.S16)
+            self._s16_valid = True
         for n in self.lin_names + [ENC + "project_features.2.weight"]:
             if self.fp32:
                 W.fwd[n] = ops.split3(S.view(n), 1)
@@ -500,9 +505,8 @@ class PretrainEngine:
         # ---- masks (host integer work, bit exact) and the device index maps
         if mask is None:
             idl = None if ids is None else [int(v) for v in (ids.tolist() if hasattr(ids, "tolist") else ids)]
-            mask = masking.pretrain_mask(seed=cfg.seed, update=num_updates, ids=idl, batch=B, frames=T, clone_batch=M,
-                                         mask_prob=self.a.mask_prob, mask_length=self.a.mask_length,
-                                         mask_dropout=self.a.mask_dropout, add_masks=self.a.add_masks)
+            mask = self._prefetcher(B, T).get(num_updates, idl) if idl is not None else \
+                masking.pretrain_mask(update=num_updates, ids=None, **self._mask_static(B, T))
         R = B * M
         assert mask.shape == (R, T)
         tk = int(T - mask[0].sum())
@@ -556,6 +560,32 @@ class PretrainEngine:
         self.ctx = c if save else None
         return {"loss_sum": loss_sum, "colstats": stats, "sample_size": n_masked, "masked_pct": 1.0 - tk / T,
                 "mask": mask, "T": T, "tk": tk}
+
+    def _mask_static(self, B: int, T: int) -> dict:
+        return dict(seed=self.cfg.seed, batch=B, frames=T, clone_batch=self.M, mask_prob=self.a.mask_prob,
+                    mask_length=self.a.mask_length, mask_dropout=self.a.mask_dropout, add_masks=self.a.add_masks)
+
+    def _prefetcher(self, B: int, T: int) -> masking.MaskPrefetcher:
+        key = (B, T)
+        pf = getattr(self, "_pf", None)
+        if pf is None or pf[0] != key:
+            if pf is not None:
+                pf[1].close()
+            pf = self._pf = (key, masking.MaskPrefetcher(**self._mask_static(B, T)))
+        return pf[1]
+
+    def frames_for(self, n_samples: int) -> int:
+        """Frames the feature extractor produces for ``n_samples`` input samples."""
+        t = n_samples
+        for (_c, k, st) in self.layers[1:]:
+            if st > 1:
+                t = (t + 2 * int(math.ceil(st / 2)) - k) // st + 1
+        return t
+
+    def prefetch_mask(self, num_updates: int, ids, batch: int, n_samples: int) -> None:
+        """Start computing the masks of a FUTURE forward(ids, num_updates) on the worker thread: they depend
+        only on (seed, update, ids), so the host numpy work overlaps the GPU step before it."""
+        self._prefetcher(batch, self.frames_for(n_samples)).announce(num_updates, [int(v) for v in ids])
 
     def _arange(self, n: int) -> torch.Tensor:
         t = getattr(self, "_arange_buf", None)
@@ -706,12 +736,11 @@ class PretrainEngine:
         """Packed-layout weight gradients -> checkpoint-layout views of the flat gradient buffer."""
         for key, buf in self.gpacked.items():
             name, _ = key.split("|")
-            P.unpack_grad(self.sp[key], buf, self.G(name))
+            P.unpack_grad(self.sp[key], buf, self.G(name))  # G += packed
+            buf.zero_()
 
     def zero_grad(self) -> None:
         self.S.grad.zero_()
-        for buf in self.gpacked.values():
-            buf.zero_()
 
     # ------------------------------------------------------------------------------------ EMA
     def ema_step(self, num_updates: int) -> float:

@@ -29,9 +29,24 @@ def _pick_block_n(n: int) -> int:
     return 256 if n % 256 == 0 or n > 512 else 128
 
 
+def _flops(d: L.GemmDesc) -> float:
+    if d.mode == 0:
+        return 2.0 * d.M * d.N * d.k_per_tap * d.taps * d.batch * d.groups
+    return 2.0 * d.M * d.N * d.red_rows * d.batch * d.taps * d.groups
+
+
 def _launch(d: L.GemmDesc, anchor: torch.Tensor) -> None:
     L.require_device(anchor)
+    L.launch_count += 1
+    tl = L.gemm_timeline
+    if tl is None:
+        L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm")
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm")
+    e1.record()
+    tl.append((e0, e1, _flops(d)))
 
 
 def _rows2d(t: torch.Tensor) -> tuple[int, int, int]:

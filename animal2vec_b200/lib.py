@@ -91,6 +91,11 @@ class GemmDesc(C.Structure):
 _lib = None
 _lock = threading.Lock()
 
+# Every C-ABI compute call launches exactly one kernel; the counter is bench.py's "gpu_launches" evidence.
+launch_count = 0
+# Optional per-GEMM timing (bench.py roofline leg): list of (start_event, end_event, flops) when enabled.
+gemm_timeline = None
+
 
 def exported_symbols() -> list[str]:
     """Every ``a2v_*`` function name declared in include/a2v_capi.h."""

@@ -76,6 +76,7 @@ def _p(t: Optional[torch.Tensor]):
 def _call(name: str, anchor: torch.Tensor, *args) -> None:
     L.require_device(anchor)
     fn = getattr(L.load(), name)
+    L.launch_count += 1
     L.check(fn(*args, L.stream_ptr()), name)
 
 
@@ -319,9 +320,12 @@ def ema_step(student: torch.Tensor, shadow: torch.Tensor, teacher_lp: Optional[t
           C.c_float(decay))
 
 
-def adamw_step(p, g, m, v, p_lp, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None) -> None:
+def adamw_step(p, g, m, v, p_lp, *, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None, wd_mask=None) -> None:
+    if wd_mask is not None:
+        assert wd_mask.dtype == torch.uint8 and wd_mask.numel() * 4 == p.numel()
     _call("a2v_adamw_step", p, _p(p), _p(g), _p(m), _p(v), _p(p_lp), C.c_int64(p.numel()), C.c_float(lr),
-          C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), int(step), _p(grad_scale))
+          C.c_float(beta1), C.c_float(beta2), C.c_float(eps), C.c_float(weight_decay), int(step), _p(grad_scale),
+          _p(wd_mask))
 
 
 def sumsq(x: torch.Tensor, out: torch.Tensor) -> None:

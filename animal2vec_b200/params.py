@@ -218,8 +218,9 @@ def materialize(p: Pack, src: torch.Tensor, fp32_mode: bool) -> torch.Tensor:
 
 
 def unpack_grad(p: Pack, packed_grad: torch.Tensor, dst: torch.Tensor) -> None:
-    """Inverse index map: write the packed-layout fp32 gradient into the reference-layout view."""
-    ops.relayout(packed_grad, dst, p.dims, p.out_strides, 0, p.in_strides, p.in_off)
+    """Inverse index map: ADD the packed-layout fp32 gradient into the reference-layout view (the packed
+    buffers are transient per backward; the flat gradient buffer is the only accumulator)."""
+    ops.relayout(packed_grad, dst, p.dims, p.out_strides, 0, p.in_strides, p.in_off, accumulate=True)
 
 
 # --------------------------------------------------------------------------------------------

@@ -200,7 +200,9 @@ int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t*
  *  a2v_ema_step: fused EMA teacher update replacing fairseq EMAModule.step + reload
  *    (called from nn/data2vec2.py:408): shadow = d*shadow + (1-d)*student, bf16 copy out.
  *  a2v_adamw_step: fairseq Adam with decoupled weight decay; grads are multiplied by the
- *    device scalar *grad_scale (clip coefficient x 1/sample_size); writes the bf16 copy.
+ *    device scalar *grad_scale (clip coefficient x 1/sample_size); writes the bf16 copy. wd_mask
+ *    (one byte per 4 parameters, or NULL) switches the decay off for the weight_decay_scale-0
+ *    group of nn/data2vec2.py:318-322 so that the whole flat buffer is one launch.
  *  a2v_sumsq / a2v_clip_coef: gradient-norm clipping without a host round trip.
  * ------------------------------------------------------------------------------------ */
 int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream);
@@ -219,7 +221,7 @@ int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_
                  a2v_stream_t stream);
 int a2v_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step, const float* grad_scale,
-                   a2v_stream_t stream);
+                   const uint8_t* wd_mask, a2v_stream_t stream);
 int a2v_sumsq(const float* x, int64_t n, double* out, a2v_stream_t stream);
 int a2v_clip_coef(const double* sumsq, const float* denom, float numer, float max_norm, float* out2,
                   a2v_stream_t stream);
