@@ -80,6 +80,39 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
     return cdf + x * pdf;
 }
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7): one rcp + one ex2 instead of erff's
+// long polynomial. Used by the bf16 kernels (the fp32 validation kernels keep erff).
+//   erf(u) = sign(u) * (1 - poly(t) * exp(-u^2)),  t = 1 / (1 + 0.3275911 |u|)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float u = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float e = __expf(-u * u);
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    const float erfa = fmaf(-pl * t, e, 1.0f);          // erf(|u|)
+    return 0.5f * x * (1.0f + copysignf(erfa, x));
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+    const float u = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float e = __expf(-u * u);                      // = exp(-x^2/2): shared by erf and the pdf
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    const float erfa = fmaf(-pl * t, e, 1.0f);
+    const float cdf = 0.5f * (1.0f + copysignf(erfa, x));
+    return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+template <typename T> __device__ __forceinline__ float gelu_t(float x);
+template <> __device__ __forceinline__ float gelu_t<float>(float x) { return gelu_exact(x); }
+template <> __device__ __forceinline__ float gelu_t<bf16>(float x) { return gelu_fast(x); }
+template <typename T> __device__ __forceinline__ float gelu_grad_t(float x);
+template <> __device__ __forceinline__ float gelu_grad_t<float>(float x) { return gelu_exact_grad(x); }
+template <> __device__ __forceinline__ float gelu_grad_t<bf16>(float x) { return gelu_fast_grad(x); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

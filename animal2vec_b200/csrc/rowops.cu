@@ -51,33 +51,133 @@ struct RowLnParams {
 __device__ __forceinline__ int param_index(int c, int gw, int gr) { return (c / gw) * gr + (c % gw); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-template <typename T, int NCH>
-__global__ void __launch_bounds__(256) rowln_fwd_kernel(const RowLnParams p) {
+// ---------------------------------------------------------------------------------------------
+// Per-warp asynchronous row pipeline. Every warp owns a ring of STAGES shared-memory slots; lane 0
+// fills a slot with up to three 1-D bulk copies (cp.async.bulk, completion on the slot's mbarrier),
+// the warp copies the landed row into registers, immediately re-arms the slot with the row STAGES
+// iterations ahead and only then does the arithmetic. Bytes in flight per SM are set by the ring
+// size (tens of KB), not by register-limited occupancy, which is what a warp-per-row LayerNorm
+// needs to reach HBM bandwidth.
+// ---------------------------------------------------------------------------------------------
+constexpr int ROWLN_WARPS = 8;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct RowPipe {
+    unsigned char* slots;  // this warp's ring: stages x ntens x row_bytes
+    uint64_t* bars;        // this warp's mbarriers [stages]
+    int stages, row_bytes, ntens;
+    const unsigned char* src[3];
+    long long rows, nwarps;
+
+    __device__ __forceinline__ void issue(int slot, long long row, int lane) {
+        if (lane == 0 && row < rows) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[slot], (uint32_t)(ntens * row_bytes));
+            unsigned char* dst = slots + (size_t)slot * ntens * row_bytes;
+            for (int t = 0; t < ntens; ++t)
+                bulk_load_1d(dst + (size_t)t * row_bytes, src[t] + row * row_bytes, (uint32_t)row_bytes, &bars[slot]);
+        }
+    }
+    __device__ __forceinline__ const unsigned char* wait(int slot, int it) {
+        mbar_wait(&bars[slot], (uint32_t)((it / stages) & 1));
+        return slots + (size_t)slot * ntens * row_bytes;
+    }
+};
+
+// shared layout: [params: nparam x C floats][rings: WARPS x stages x ntens x row_bytes][mbarriers]
+template <typename T>
+__device__ __forceinline__ RowPipe make_pipe(unsigned char* smem, int nparam_floats, int C, int stages, int ntens,
+                                             const void* s0, const void* s1, const void* s2, long long rows,
+                                             long long nwarps, long long warp0, int lane) {
+    RowPipe rp;
+    const int warp = threadIdx.x >> 5;
+    rp.stages = stages;
+    rp.ntens = ntens;
+    rp.row_bytes = C * (int)sizeof(T);
+    unsigned char* rings = smem + (size_t)nparam_floats * sizeof(float);
+    rp.slots = rings + (size_t)warp * stages * ntens * rp.row_bytes;
+    rp.bars = reinterpret_cast<uint64_t*>(rings + (size_t)ROWLN_WARPS * stages * ntens * rp.row_bytes) + warp * stages;
+    rp.src[0] = reinterpret_cast<const unsigned char*>(s0);
+    rp.src[1] = reinterpret_cast<const unsigned char*>(s1);
+    rp.src[2] = reinterpret_cast<const unsigned char*>(s2);
+    rp.rows = rows;
+    rp.nwarps = nwarps;
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&rp.bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    for (int s = 0; s < stages; ++s) rp.issue(s, warp0 + (long long)s * nwarps, lane);
+    return rp;
+}
+
+// stored-channel-indexed parameter tables in shared memory (pads -> 0): no index math in the row loop
+__device__ __forceinline__ void fill_param_table(float* dst, const float* src, int C, int gw, int gr, bool padded) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const bool real = !padded || (c % gw) < gr;
+        dst[c] = (src != nullptr && real) ? src[padded ? param_index(c, gw, gr) : c] : 0.f;
+    }
+}
+
+template <typename T, int NCH, bool FULL, int ACT, bool AFFINE>
+__global__ void __launch_bounds__(256) rowln_fwd_kernel(const RowLnParams p, const int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
     const int C = p.C;
     const bool padded = p.gr < p.gw;
-    int creal = (C / p.gw) * p.gr;
+    const int creal = (C / p.gw) * p.gr;
     const float inv_c = 1.0f / (float)creal;
     const float keep_b = p.drop_b > 0.f ? 1.0f / (1.0f - p.drop_b) : 1.0f;
     const float keep_o = p.drop_out > 0.f ? 1.0f / (1.0f - p.drop_out) : 1.0f;
-    const T* A = reinterpret_cast<const T*>(p.a);
-    const T* Bp = reinterpret_cast<const T*>(p.b);
-    const T* P = reinterpret_cast<const T*>(p.post);
     T* Y = reinterpret_cast<T*>(p.y);
+    const bool has_b = p.b != nullptr, has_post = p.post != nullptr;
+    constexpr bool affine = AFFINE;
 
-    for (long long row = warp0; row < p.rows; row += nwarps) {
-        float z[NCH][4];
-        float s = 0.f;
+    float* tab = reinterpret_cast<float*>(smem_raw);  // [gamma | beta | act_alpha | act_beta] x C
+    fill_param_table(tab, p.gamma, C, p.gw, p.gr, padded);
+    fill_param_table(tab + C, p.beta, C, p.gw, p.gr, padded);
+    fill_param_table(tab + 2 * C, p.act_alpha, C, p.gw, p.gr, padded);
+    fill_param_table(tab + 3 * C, p.act_beta, C, p.gw, p.gr, padded);
+    // per-lane pad masks (bit j of nibble i): depends on the channel only, hoisted out of the row loop
+    unsigned realmask = 0;  // FULL: every stored channel of every chunk is real, the tests fold away
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (lane + 32 * i) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (FULL || (c + j < C && (!padded || ((c + j) % p.gw) < p.gr))) realmask |= 1u << (4 * i + j);
+    }
+#define RL_REAL(i, j) (FULL || ((realmask >> (4 * (i) + (j))) & 1u))
+    __syncthreads();
+
+    const int ntens = 1 + (has_b ? 1 : 0) + (has_post ? 1 : 0);
+    RowPipe rp = make_pipe<T>(smem_raw, 4 * C, C, stages, ntens, p.a, has_b ? p.b : p.post, p.post, p.rows, nwarps,
+                              warp0, lane);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        const unsigned char* sm = rp.wait(slot, it);
+        const T* sa = reinterpret_cast<const T*>(sm);
+        const T* sb = reinterpret_cast<const T*>(sm + rp.row_bytes);
+        const T* sp = reinterpret_cast<const T*>(sm + (size_t)(has_b ? 2 : 1) * rp.row_bytes);
+        float z[NCH][4], post[NCH][4];
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int c = (lane + 32 * i) * 4;
-            if (c < C) {
-                load4(A + row * C + c, z[i]);
-                if (Bp != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) z[i][j] = post[i][j] = 0.f;
+            if (FULL || c < C) {
+                load4(sa + c, z[i]);
+                if (has_b) {
                     float t[4];
-                    load4(Bp + row * C + c, t);
+                    load4(sb + c, t);
                     if (p.drop_b > 0.f) {
                         bool k[4];
                         drop_keep4(p.seed_b, (unsigned long long)(row * C + c) >> 2, p.drop_b, k);
@@ -87,32 +187,29 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const RowLnParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) z[i][j] += t[j];
                 }
-                if (padded) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (((c + j) % p.gw) >= p.gr) z[i][j] = 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) s += z[i][j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) z[i][j] = 0.f;
+                if (has_post) load4(sp + c, post[i]);
             }
         }
+        __syncwarp();
+        rp.issue(slot, row + (long long)stages * nwarps, lane);  // slot is in registers now: re-arm it
+
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (!RL_REAL(i, j)) z[i][j] = 0.f;
+                s += z[i][j];
+            }
         const float mean = warp_sum(s) * inv_c;
         float v = 0.f;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) {
-            const int c = (lane + 32 * i) * 4;
-            if (c < C) {
+        for (int i = 0; i < NCH; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const bool real = !padded || ((c + j) % p.gw) < p.gr;
-                    const float d = z[i][j] - mean;
-                    v += real ? d * d : 0.f;
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float d = z[i][j] - mean;
+                v += RL_REAL(i, j) ? d * d : 0.f;
             }
-        }
         const float rstd = rsqrtf(warp_sum(v) * inv_c + p.eps);
         if (lane == 0) {
             if (p.mean != nullptr) p.mean[row] = mean;
@@ -121,28 +218,30 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const RowLnParams p) {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int c = (lane + 32 * i) * 4;
-            if (c < C) {
+            if (FULL || c < C) {
                 float o[4];
                 bool ko[4] = {true, true, true, true};
                 if (p.drop_out > 0.f) drop_keep4(p.seed_out, (unsigned long long)(row * C + c) >> 2, p.drop_out, ko);
-                float post[4] = {0.f, 0.f, 0.f, 0.f};
-                if (P != nullptr) load4(P + row * C + c, post);
+                float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+                if (affine) {
+                    load4(tab + c, ga);
+                    load4(tab + C + c, be);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const bool real = !padded || ((c + j) % p.gw) < p.gr;
-                    const int pi = padded ? param_index(c + j, p.gw, p.gr) : (c + j);
+                    const bool real = RL_REAL(i, j);
                     float n = (z[i][j] - mean) * rstd;
-                    if (p.gamma != nullptr) n = n * p.gamma[real ? pi : 0] + (p.beta != nullptr ? p.beta[real ? pi : 0] : 0.f);
+                    if (affine) n = n * ga[j] + be[j];
                     float y;
-                    if (p.act == 1) {
-                        y = gelu_exact(n);
-                    } else if (p.act == 2) {
-                        y = n * p.act_alpha[real ? pi : 0] * sigmoidf_(p.act_beta[real ? pi : 0] * n);
+                    if (ACT == 1) {
+                        y = gelu_t<T>(n);
+                    } else if (ACT == 2) {
+                        y = n * tab[2 * C + c + j] * sigmoidf_(tab[3 * C + c + j] * n);
                     } else {
                         y = n;
                     }
                     if (p.drop_out > 0.f) y = ko[j] ? y * keep_o : 0.f;
-                    y += post[j];
+                    y += post[i][j];
                     o[j] = real ? y : 0.f;
                 }
                 store4(Y + row * C + c, o);
@@ -151,50 +250,70 @@ __global__ void __launch_bounds__(256) rowln_fwd_kernel(const RowLnParams p) {
     }
 }
 
-template <typename T, int NCH>
-__global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p) {
-    extern __shared__ float sred[];  // [4][C] partial parameter gradients
+template <typename T, int NCH, bool FULL, int ACT, bool AFFINE>
+__global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p, const int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
-    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
     const int C = p.C;
     const bool padded = p.gr < p.gw;
     const int creal = (C / p.gw) * p.gr;
     const float inv_c = 1.0f / (float)creal;
     const float keep_b = p.drop_b > 0.f ? 1.0f / (1.0f - p.drop_b) : 1.0f;
     const float keep_o = p.drop_out > 0.f ? 1.0f / (1.0f - p.drop_out) : 1.0f;
-    const T* A = reinterpret_cast<const T*>(p.a);
-    const T* Bp = reinterpret_cast<const T*>(p.b);
-    const T* DY = reinterpret_cast<const T*>(p.dy);
     T* DA = reinterpret_cast<T*>(p.da);
     T* DB = reinterpret_cast<T*>(p.db);
-    const bool want_affine = p.dgamma != nullptr;
-    const bool want_act = p.dact_alpha != nullptr;
+    const bool has_b = p.b != nullptr;
+    constexpr bool affine = AFFINE;
+    const bool want_affine = AFFINE && p.dgamma != nullptr;
+    const bool want_act = ACT == 2 && p.dact_alpha != nullptr;
 
+    float* tab = reinterpret_cast<float*>(smem_raw);  // [gamma | beta | act_alpha | act_beta] x C
+    float* sred = tab + 4 * C;                         // [dgamma | dbeta | dalpha | dabeta] x C partials
+    fill_param_table(tab, p.gamma, C, p.gw, p.gr, padded);
+    fill_param_table(tab + C, p.beta, C, p.gw, p.gr, padded);
+    fill_param_table(tab + 2 * C, p.act_alpha, C, p.gw, p.gr, padded);
+    fill_param_table(tab + 3 * C, p.act_beta, C, p.gw, p.gr, padded);
     for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) sred[i] = 0.f;
+    unsigned realmask = 0;  // FULL: every stored channel of every chunk is real, the tests fold away
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int c = (lane + 32 * i) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (FULL || (c + j < C && (!padded || ((c + j) % p.gw) < p.gr))) realmask |= 1u << (4 * i + j);
+    }
+#define RL_REAL(i, j) (FULL || ((realmask >> (4 * (i) + (j))) & 1u))
     __syncthreads();
 
-    float acc_g[NCH][4], acc_b[NCH][4];
+    constexpr int NACC = AFFINE ? NCH : 1;
+    float acc_g[NACC][4], acc_b[NACC][4];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
+    for (int i = 0; i < NACC; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc_g[i][j] = acc_b[i][j] = 0.f;
 
-    for (long long row = warp0; row < p.rows; row += nwarps) {
+    const int ntens = has_b ? 3 : 2;
+    RowPipe rp = make_pipe<T>(smem_raw, 8 * C, C, stages, ntens, p.a, p.dy, p.b, p.rows, nwarps, warp0, lane);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        const unsigned char* sm = rp.wait(slot, it);
+        const T* sa = reinterpret_cast<const T*>(sm);
+        const T* sdy = reinterpret_cast<const T*>(sm + rp.row_bytes);
+        const T* sb = reinterpret_cast<const T*>(sm + (size_t)2 * rp.row_bytes);
         float xh[NCH][4], g[NCH][4];
-        const float mean = p.mean[row], rstd = p.rstd[row];
-        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int c = (lane + 32 * i) * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) xh[i][j] = g[i][j] = 0.f;
-            if (c < C) {
-                float z[4], dy[4];
-                load4(A + row * C + c, z);
-                if (Bp != nullptr) {
+            if (FULL || c < C) {
+                load4(sa + c, xh[i]);  // z for now
+                if (has_b) {
                     float t[4];
-                    load4(Bp + row * C + c, t);
+                    load4(sb + c, t);
                     if (p.drop_b > 0.f) {
                         bool k[4];
                         drop_keep4(p.seed_b, (unsigned long long)(row * C + c) >> 2, p.drop_b, k);
@@ -202,46 +321,60 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p) {
                         for (int j = 0; j < 4; ++j) t[j] = k[j] ? t[j] * keep_b : 0.f;
                     }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) z[j] += t[j];
+                    for (int j = 0; j < 4; ++j) xh[i][j] += t[j];
                 }
-                load4(DY + row * C + c, dy);
+                load4(sdy + c, g[i]);  // dy for now
+            }
+        }
+        __syncwarp();
+        rp.issue(slot, row + (long long)stages * nwarps, lane);
+
+        const float mean = p.mean[row], rstd = p.rstd[row];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            const int c = (lane + 32 * i) * 4;
+            if (FULL || c < C) {
                 if (p.drop_out > 0.f) {
                     bool ko[4];
                     drop_keep4(p.seed_out, (unsigned long long)(row * C + c) >> 2, p.drop_out, ko);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) dy[j] = ko[j] ? dy[j] * keep_o : 0.f;
+                    for (int j = 0; j < 4; ++j) g[i][j] = ko[j] ? g[i][j] * keep_o : 0.f;
+                }
+                float ga[4] = {1.f, 1.f, 1.f, 1.f}, be[4] = {0.f, 0.f, 0.f, 0.f};
+                if (affine) {
+                    load4(tab + c, ga);
+                    load4(tab + C + c, be);
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const bool real = !padded || ((c + j) % p.gw) < p.gr;
-                    if (!real) continue;
-                    const int pi = padded ? param_index(c + j, p.gw, p.gr) : (c + j);
-                    const float x = (z[j] - mean) * rstd;
-                    const float gam = p.gamma != nullptr ? p.gamma[pi] : 1.f;
-                    const float n = x * gam + (p.beta != nullptr ? p.beta[pi] : 0.f);
+                    const bool real = RL_REAL(i, j);
+                    const float dyv = g[i][j];
+                    const float x = (xh[i][j] - mean) * rstd;
+                    const float n = x * ga[j] + be[j];
                     float dn;
-                    if (p.act == 1) {
-                        dn = dy[j] * gelu_exact_grad(n);
-                    } else if (p.act == 2) {
-                        const float al = p.act_alpha[pi], be = p.act_beta[pi];
-                        const float sg = sigmoidf_(be * n);
-                        dn = dy[j] * al * (sg + n * be * sg * (1.f - sg));
-                        if (want_act) {
-                            // reuse acc_* of the (unused when act==2 has its own) slots below
-                            atomicAdd(&sred[2 * C + c + j], dy[j] * n * sg);
-                            atomicAdd(&sred[3 * C + c + j], dy[j] * al * n * n * sg * (1.f - sg));
+                    if (ACT == 1) {
+                        dn = dyv * gelu_grad_t<T>(n);
+                    } else if (ACT == 2) {
+                        const float al = tab[2 * C + c + j], bt = tab[3 * C + c + j];
+                        const float sg = sigmoidf_(bt * n);
+                        dn = dyv * al * (sg + n * bt * sg * (1.f - sg));
+                        if (want_act && real) {
+                            atomicAdd(&sred[2 * C + c + j], dyv * n * sg);
+                            atomicAdd(&sred[3 * C + c + j], dyv * al * n * n * sg * (1.f - sg));
                         }
                     } else {
-                        dn = dy[j];
+                        dn = dyv;
                     }
-                    if (want_affine) {
-                        acc_g[i][j] += dn * x;
-                        acc_b[i][j] += dn;
+                    if (!real) dn = 0.f;
+                    if (AFFINE) {
+                        acc_g[AFFINE ? i : 0][j] += dn * x;
+                        acc_b[AFFINE ? i : 0][j] += dn;
                     }
-                    xh[i][j] = x;
-                    g[i][j] = dn * gam;
+                    xh[i][j] = real ? x : 0.f;
+                    g[i][j] = dn * ga[j];
                     s1 += g[i][j];
-                    s2 += g[i][j] * x;
+                    s2 += g[i][j] * xh[i][j];
                 }
             }
         }
@@ -250,11 +383,11 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p) {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int c = (lane + 32 * i) * 4;
-            if (c < C) {
+            if (FULL || c < C) {
                 float dz[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const bool real = !padded || ((c + j) % p.gw) < p.gr;
+                    const bool real = RL_REAL(i, j);
                     dz[j] = real ? rstd * (g[i][j] - s1 - xh[i][j] * s2) : 0.f;
                 }
                 if (DA != nullptr) store4(DA + row * C + c, dz);
@@ -274,11 +407,11 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p) {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             const int c = (lane + 32 * i) * 4;
-            if (c < C) {
+            if (FULL || c < C) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    atomicAdd(&sred[c + j], acc_g[i][j]);
-                    atomicAdd(&sred[C + c + j], acc_b[i][j]);
+                    atomicAdd(&sred[c + j], acc_g[AFFINE ? i : 0][j]);
+                    atomicAdd(&sred[C + c + j], acc_b[AFFINE ? i : 0][j]);
                 }
             }
         }
@@ -302,31 +435,76 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p) {
 template <typename T>
 static int launch_rowln(const RowLnParams& p, bool bwd, cudaStream_t st) {
     const int nch = ceil_div(p.C, 128);
-    const int threads = 256;
-    long long blocks_needed = ceil_div64(p.rows, threads / 32);
-    int grid = (int)(blocks_needed < (long long)a2v_num_sms() * 8 ? blocks_needed : (long long)a2v_num_sms() * 8);
+    const bool full = (p.gr == p.gw) && (p.C == 128 || p.C == 256 || p.C == 512 || p.C == 1024);
+    const int threads = ROWLN_WARPS * 32;
+    const int row_bytes = p.C * (int)sizeof(T);
+    const int ntens = bwd ? (p.b != nullptr ? 3 : 2) : (1 + (p.b != nullptr ? 1 : 0) + (p.post != nullptr ? 1 : 0));
+    const size_t fixed = (size_t)(bwd ? 8 : 4) * p.C * sizeof(float) + (size_t)ROWLN_WARPS * 8 * 8;
+    const size_t per_stage = (size_t)ROWLN_WARPS * ntens * row_bytes;
+    // forward kernels fit two CTAs per SM (about 104 registers): keep each under ~110 KB; the
+    // backward kernel is register-limited to one CTA per SM and may take up to ~200 KB.
+    const bool one_cta = bwd && p.gamma != nullptr;  // affine backward: ~220 registers (parameter-gradient accumulators)
+    const size_t budget = one_cta ? 200 * 1024 : 110 * 1024;
+    int stages = (int)((budget > fixed ? budget - fixed : 0) / per_stage);
+    if (stages < 2) stages = 2;
+    if (stages > 6) stages = 6;
+    const size_t smem = fixed + per_stage * stages;
+    A2V_REQUIRE(smem <= 227 * 1024, "rowln: row of %d channels does not fit the shared-memory pipeline", p.C);
+    const int ctas_per_sm = one_cta ? 1 : (smem <= 113 * 1024 ? 2 : 1);
+    long long blocks_needed = ceil_div64(p.rows, ROWLN_WARPS);
+    long long cap = (long long)a2v_num_sms() * ctas_per_sm;
+    int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
     if (grid < 1) grid = 1;
-    const size_t smem = bwd ? (size_t)4 * p.C * sizeof(float) : 0;
-#define A2V_ROWLN(N)                                                          \
-    do {                                                                      \
-        if (bwd)                                                              \
-            rowln_bwd_kernel<T, N><<<grid, threads, smem, st>>>(p);          \
-        else                                                                  \
-            rowln_fwd_kernel<T, N><<<grid, threads, 0, st>>>(p);             \
+#define A2V_ROWLN_K(N, F, A, AF)                                                                           \
+    do {                                                                                                  \
+        auto kf = rowln_fwd_kernel<T, N, F, A, AF>;                                                       \
+        auto kb = rowln_bwd_kernel<T, N, F, A, AF>;                                                       \
+        static size_t conf_arr[2] = {0, 0};                                                               \
+        size_t& conf = conf_arr[bwd ? 1 : 0];                                                             \
+        if (smem > conf) {                                                                                \
+            cudaError_t e = bwd ? cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) \
+                                : cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) {                                                                       \
+                a2v_set_error("rowln: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e)); \
+                return A2V_ERR_CUDA;                                                                      \
+            }                                                                                             \
+            conf = smem;                                                                                  \
+        }                                                                                                 \
+        if (bwd)                                                                                          \
+            kb<<<grid, threads, smem, st>>>(p, stages);                                                   \
+        else                                                                                              \
+            kf<<<grid, threads, smem, st>>>(p, stages);                                                   \
     } while (0)
+#define A2V_ROWLN_F(N, F)                                                       \
+    do {                                                                        \
+        if (p.act == 2) A2V_ROWLN_K(N, false, 2, true);                         \
+        else if (p.act == 1 && affine_) A2V_ROWLN_K(N, F, 1, true);             \
+        else if (p.act == 1) A2V_ROWLN_K(N, F, 1, false);                       \
+        else if (affine_) A2V_ROWLN_K(N, F, 0, true);                           \
+        else A2V_ROWLN_K(N, F, 0, false);                                       \
+    } while (0)
+#define A2V_ROWLN(N)                                  \
+    do {                                              \
+        if (full) A2V_ROWLN_F(N, true);               \
+        else A2V_ROWLN_F(N, false);                   \
+    } while (0)
+    const bool affine_ = p.gamma != nullptr;
+    A2V_REQUIRE(p.act != 2 || (affine_ && !full), "rowln: PSwish is built for the affine, padded 127-of-128 case");
+    A2V_REQUIRE(affine_ || p.beta == nullptr, "rowln: beta without gamma");
     if (nch <= 1) A2V_ROWLN(1);
     else if (nch <= 2) A2V_ROWLN(2);
     else if (nch <= 4) A2V_ROWLN(4);
-    else if (nch <= 6) A2V_ROWLN(6);
     else A2V_ROWLN(8);
+#undef A2V_ROWLN_K
+#undef A2V_ROWLN_F
 #undef A2V_ROWLN
     return a2v_check_launch(bwd ? "rowln_bwd" : "rowln_fwd");
 }
 
 static int validate_rowln(const a2v_rowln_desc* d) {
     A2V_REQUIRE(d != nullptr, "rowln: NULL descriptor");
-    A2V_REQUIRE(d->rows >= 0 && d->channels > 0 && d->channels % 4 == 0 && d->channels <= 1024,
-                "rowln: channels must be a multiple of 4 in (0, 1024], got %d", d->channels);
+    A2V_REQUIRE(d->rows >= 0 && d->channels > 0 && d->channels % 8 == 0 && d->channels <= 1024,
+                "rowln: channels must be a multiple of 8 in (0, 1024], got %d", d->channels);
     A2V_REQUIRE(d->group_width > 0 && d->group_real > 0 && d->group_real <= d->group_width &&
                     d->channels % d->group_width == 0,
                 "rowln: bad group padding (%d real of %d, C=%d)", d->group_real, d->group_width, d->channels);
