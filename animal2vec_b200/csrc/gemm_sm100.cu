@@ -87,7 +87,8 @@ struct GemmSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
+    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;  // 4 epilogue warps x 32 rows x EPI_PITCH floats
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024: alignment slack
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
 
@@ -109,71 +110,107 @@ __device__ __forceinline__ void store32(T* p, const float (&v)[32]) {
     }
 }
 
-// Epilogue for one 32-column chunk of one accumulator row.
-template <typename TC>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], long long row_off, int gcol0,
-                                               int ncols_valid) {
-    TC* c = reinterpret_cast<TC*>(p.c) + row_off + gcol0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
-    if (p.bias != nullptr) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-            if (i < ncols_valid) v[i] += __ldg(p.bias + gcol0 + i);
-    }
-    const bool full = (ncols_valid == 32);
-    if (p.preact != nullptr) {
-        TC* u = reinterpret_cast<TC*>(p.preact) + row_off + gcol0;
+// Epilogue for one 32-column chunk of 32 accumulator rows, in the COALESCED layout produced by the
+// shared-memory transpose: lane l holds columns 4*(l&7) .. +3 of rows (l>>3) + 4*i, i = 0..7 in
+// v[4*i .. 4*i+3]. A warp-level access therefore touches 4 rows x 128 contiguous bytes (fp32) or
+// 4 rows x 64 bytes (bf16): full sectors, 4 lines per instruction instead of 32.
+constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4): conflict-free for both access patterns
+
+// Compile-time epilogue selection: EPI >= 0 is a bit mask (the hot variants, straight-line code that
+// fits the instruction cache); EPI < 0 reads the descriptor at run time (every other combination).
+constexpr int EPI_BIAS = 1, EPI_PREACT = 2, EPI_GELU = 4, EPI_DGELU = 8, EPI_RES = 16;
+template <int EPI> __device__ __forceinline__ bool epi_bias(const GemmParams& p) { return EPI < 0 ? p.bias != nullptr : (EPI & EPI_BIAS) != 0; }
+template <int EPI> __device__ __forceinline__ bool epi_preact(const GemmParams& p) { return EPI < 0 ? p.preact != nullptr : (EPI & EPI_PREACT) != 0; }
+template <int EPI> __device__ __forceinline__ bool epi_gelu(const GemmParams& p) { return EPI < 0 ? p.act == 1 : (EPI & EPI_GELU) != 0; }
+template <int EPI> __device__ __forceinline__ bool epi_dgelu(const GemmParams& p) { return EPI < 0 ? p.dgelu_u != nullptr : (EPI & EPI_DGELU) != 0; }
+template <int EPI> __device__ __forceinline__ bool epi_res(const GemmParams& p) { return EPI < 0 ? p.residual != nullptr : (EPI & EPI_RES) != 0; }
+
+template <typename TC, int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], long long row_off0, int rows_ok,
+                                               int gcol, int cols_ok, int lane) {
+    // row_off0: element offset of the warp's first row; rows_ok: number of valid rows (<= 32) from it;
+    // gcol: global column of this lane's first element; cols_ok: valid columns from gcol (may be <= 0)
+    const int rsub = lane >> 3;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool full = cols_ok >= 4;
+    if (epi_bias<EPI>(p) && cols_ok > 0) {
         if (full) {
-            store32(u, v);
+            load4(p.bias + gcol, bias);
         } else {
-            for (int i = 0; i < ncols_valid; ++i) u[i] = from_f32<TC>(v[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cols_ok) bias[j] = p.bias[gcol + j];
         }
     }
-    if (p.act == 1) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_exact(v[i]);
-    }
-    if (p.dgelu_u != nullptr) {
-        const TC* u = reinterpret_cast<const TC*>(p.dgelu_u) + row_off + gcol0;
-        float t[32];
-        if (full) {
-            load32(u, t);
-        } else {
-            for (int i = 0; i < 32; ++i) t[i] = (i < ncols_valid) ? to_f32(u[i]) : 0.f;
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        if (r >= rows_ok || cols_ok <= 0) continue;
+        const long long off = row_off0 + (long long)r * p.ldc + gcol;
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = v[4 * i + j] * p.alpha + bias[j];
+        if (epi_preact<EPI>(p)) {
+            TC* u = reinterpret_cast<TC*>(p.preact) + off;
+            if (full) store4(u, x);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < cols_ok) u[j] = from_f32<TC>(x[j]);
+            }
         }
+        if (epi_gelu<EPI>(p)) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= gelu_exact_grad(t[i]);
-    }
-    if (p.residual != nullptr) {
-        const TC* r = reinterpret_cast<const TC*>(p.residual) + row_off + gcol0;
-        float t[32];
-        if (full) {
-            load32(r, t);
-        } else {
-            for (int i = 0; i < 32; ++i) t[i] = (i < ncols_valid) ? to_f32(r[i]) : 0.f;
+            for (int j = 0; j < 4; ++j) x[j] = gelu_exact(x[j]);
         }
+        if (epi_dgelu<EPI>(p)) {
+            const TC* u = reinterpret_cast<const TC*>(p.dgelu_u) + off;
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full) load4(u, t);
+            else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += t[i];
-    }
-    if (full) {
-        store32(c, v);
-    } else {
-        for (int i = 0; i < ncols_valid; ++i) c[i] = from_f32<TC>(v[i]);
+                for (int j = 0; j < 4; ++j) if (j < cols_ok) t[j] = to_f32(u[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] *= gelu_exact_grad(t[j]);
+        }
+        if (epi_res<EPI>(p)) {
+            const TC* rr = reinterpret_cast<const TC*>(p.residual) + off;
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full) load4(rr, t);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (j < cols_ok) t[j] = to_f32(rr[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] += t[j];
+        }
+        TC* c = reinterpret_cast<TC*>(p.c) + off;
+        if (full) store4(c, x);
+        else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cols_ok) c[j] = from_f32<TC>(x[j]);
+        }
     }
 }
 
-__device__ __forceinline__ void epilogue_chunk_f32_accum(const GemmParams& p, float (&v)[32], long long row_off,
-                                                         int gcol0, int ncols_valid) {
-    float* c = reinterpret_cast<float*>(p.c) + row_off + gcol0;
-    if (p.out_atomic) {
-        for (int i = 0; i < ncols_valid; ++i) atomicAdd(c + i, v[i] * p.alpha);
-    } else {
-        for (int i = 0; i < ncols_valid; ++i) c[i] += v[i] * p.alpha;
+__device__ __forceinline__ void epilogue_chunk_f32_accum(const GemmParams& p, float (&v)[32], long long row_off0,
+                                                         int rows_ok, int gcol, int cols_ok, int lane) {
+    const int rsub = lane >> 3;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        if (r >= rows_ok || cols_ok <= 0) continue;
+        float* c = reinterpret_cast<float*>(p.c) + row_off0 + (long long)r * p.ldc + gcol;
+        if (p.out_atomic) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cols_ok) atomicAdd(c + j, v[4 * i + j] * p.alpha);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cols_ok) c[j] += v[4 * i + j] * p.alpha;
+        }
     }
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
@@ -185,6 +222,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull_bar = empty_bar + S::STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* epi_stage = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -302,7 +340,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else {
         // ------------------------------------------------------------ epilogue warps
         const int q = warp & 3;  // TMEM lane quarter this warp may access
-        const int r = q * 32 + lane;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -311,37 +348,54 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tile_k_range(p, t, kb0, kb1);
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-            const int row_in_block = t.m_tile * BLOCK_M + r;
-            const bool row_ok = row_in_block < p.M;
+            const int row0_in_block = t.m_tile * BLOCK_M + q * 32;  // first row of this warp's 32-row slab
+            int rows_ok = p.M - row0_in_block;
+            rows_ok = rows_ok > 32 ? 32 : rows_ok;
             long long row_g;
             int col_base;
             if (MODE == 0) {
-                row_g = (long long)t.b * p.c_batch_stride + p.c_row_off + row_in_block;
+                row_g = (long long)t.b * p.c_batch_stride + p.c_row_off + row0_in_block;
                 col_base = t.g * p.c_group_stride;
             } else {
-                row_g = (long long)t.g * p.c_group_stride + row_in_block;
+                row_g = (long long)t.g * p.c_group_stride + row0_in_block;
                 col_base = t.tap * p.c_tap_stride;
             }
-            const long long row_off = row_g * p.ldc;
+            const long long row_off0 = row_g * p.ldc;
             const bool has_work = (kb1 > kb0);
+            const uint32_t st = smem_u32(epi_stage + (warp - 2) * (32 * EPI_PITCH));
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t raw[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, raw);
                 tmem_ld_wait();
                 const int col0 = t.n_tile * BLOCK_N + c * 32;
-                int nvalid = p.N - col0;
-                nvalid = nvalid > 32 ? 32 : nvalid;
-                if (row_ok && nvalid > 0 && has_work) {
-                    float v[32];
+                if (col0 >= p.N) break;
+                // transpose through shared memory: thread = row  ->  8 lanes per row, 4 columns each
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-                    if (p.out_atomic || p.out_accumulate) {
-                        epilogue_chunk_f32_accum(p, v, row_off, col_base + col0, nvalid);
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (lane * EPI_PITCH + 4 * j) * 4),
+                                 "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                                 : "r"(st + (((lane >> 3) + 4 * i) * EPI_PITCH + (lane & 7) * 4) * 4)
+                                 : "memory");
+                __syncwarp();
+                const int lcol = col0 + (lane & 7) * 4;
+                const int cols_ok = p.N - lcol;
+                if (rows_ok > 0 && has_work) {
+                    if (EPI >= 0) {
+                        epilogue_chunk<bf16, EPI>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
+                    } else if (p.out_atomic || p.out_accumulate) {
+                        epilogue_chunk_f32_accum(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     } else if (p.c_f32) {
-                        epilogue_chunk<float>(p, v, row_off, col_base + col0, nvalid);
+                        epilogue_chunk<float, -1>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     } else {
-                        epilogue_chunk<bf16>(p, v, row_off, col_base + col0, nvalid);
+                        epilogue_chunk<bf16, -1>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     }
                 }
             }
@@ -412,11 +466,11 @@ static int make_map(CUtensorMap* m, const a2v_operand& o, int box_rows, const ch
     return A2V_OK;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BLOCK_N>;
     static bool configured = false;
-    auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE>;
+    auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, EPI>;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) {
@@ -509,8 +563,21 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         if ((rc = make_map(&tb, d->b, 64, "B")) != A2V_OK) return rc;
     }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define A2V_DISPATCH(BN)                                                         \
-    (d->mode == 0 ? launch_gemm<BN, 0>(ta, tb, p, st) : launch_gemm<BN, 1>(ta, tb, p, st))
+    // hot bf16-output epilogues get straight-line code; everything else takes the run-time path
+    int epi = -1;
+    if (d->mode == 0 && d->c_dtype == A2V_BF16 && !d->out_atomic && !d->out_accumulate) {
+        const int m = (d->bias ? EPI_BIAS : 0) | (d->preact ? EPI_PREACT : 0) | (d->act == 1 ? EPI_GELU : 0) |
+                      (d->dgelu_u ? EPI_DGELU : 0) | (d->residual ? EPI_RES : 0);
+        if (m == 0 || m == EPI_BIAS || m == (EPI_BIAS | EPI_GELU | EPI_PREACT) || m == EPI_DGELU || m == EPI_RES) epi = m;
+    }
+#define A2V_DISPATCH(BN)                                                                              \
+    (d->mode == 1 ? launch_gemm<BN, 1, -1>(ta, tb, p, st)                                             \
+     : epi == 0 ? launch_gemm<BN, 0, 0>(ta, tb, p, st)                                                \
+     : epi == EPI_BIAS ? launch_gemm<BN, 0, EPI_BIAS>(ta, tb, p, st)                                  \
+     : epi == (EPI_BIAS | EPI_GELU | EPI_PREACT) ? launch_gemm<BN, 0, (EPI_BIAS | EPI_GELU | EPI_PREACT)>(ta, tb, p, st) \
+     : epi == EPI_DGELU ? launch_gemm<BN, 0, EPI_DGELU>(ta, tb, p, st)                                \
+     : epi == EPI_RES ? launch_gemm<BN, 0, EPI_RES>(ta, tb, p, st)                                    \
+     : launch_gemm<BN, 0, -1>(ta, tb, p, st))
     if (d->block_n == 64) return A2V_DISPATCH(64);
     if (d->block_n == 128) return A2V_DISPATCH(128);
     return A2V_DISPATCH(256);
