@@ -159,7 +159,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
         }
         if (epi_gelu<EPI>(p)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = gelu_exact(x[j]);
+            for (int j = 0; j < 4; ++j) x[j] = gelu_t<TC>(x[j]);
         }
         if (epi_dgelu<EPI>(p)) {
             const TC* u = reinterpret_cast<const TC*>(p.dgelu_u) + off;
@@ -170,7 +170,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[3
                 for (int j = 0; j < 4; ++j) if (j < cols_ok) t[j] = to_f32(u[j]);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] *= gelu_exact_grad(t[j]);
+            for (int j = 0; j < 4; ++j) x[j] *= gelu_grad_t<TC>(t[j]);
         }
         if (epi_res<EPI>(p)) {
             const TC* rr = reinterpret_cast<const TC*>(p.residual) + off;
@@ -568,13 +568,16 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
     if (d->mode == 0 && d->c_dtype == A2V_BF16 && !d->out_atomic && !d->out_accumulate) {
         const int m = (d->bias ? EPI_BIAS : 0) | (d->preact ? EPI_PREACT : 0) | (d->act == 1 ? EPI_GELU : 0) |
                       (d->dgelu_u ? EPI_DGELU : 0) | (d->residual ? EPI_RES : 0);
-        if (m == 0 || m == EPI_BIAS || m == (EPI_BIAS | EPI_GELU | EPI_PREACT) || m == EPI_DGELU || m == EPI_RES) epi = m;
+        if (m == 0 || m == EPI_BIAS || m == (EPI_BIAS | EPI_GELU | EPI_PREACT) || m == (EPI_BIAS | EPI_GELU) ||
+            m == EPI_DGELU || m == EPI_RES)
+            epi = m;
     }
 #define A2V_DISPATCH(BN)                                                                              \
     (d->mode == 1 ? launch_gemm<BN, 1, -1>(ta, tb, p, st)                                             \
      : epi == 0 ? launch_gemm<BN, 0, 0>(ta, tb, p, st)                                                \
      : epi == EPI_BIAS ? launch_gemm<BN, 0, EPI_BIAS>(ta, tb, p, st)                                  \
      : epi == (EPI_BIAS | EPI_GELU | EPI_PREACT) ? launch_gemm<BN, 0, (EPI_BIAS | EPI_GELU | EPI_PREACT)>(ta, tb, p, st) \
+     : epi == (EPI_BIAS | EPI_GELU) ? launch_gemm<BN, 0, (EPI_BIAS | EPI_GELU)>(ta, tb, p, st)        \
      : epi == EPI_DGELU ? launch_gemm<BN, 0, EPI_DGELU>(ta, tb, p, st)                                \
      : epi == EPI_RES ? launch_gemm<BN, 0, EPI_RES>(ta, tb, p, st)                                    \
      : launch_gemm<BN, 0, -1>(ta, tb, p, st))

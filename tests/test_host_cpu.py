@@ -1,0 +1,211 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every symbol include/a2v_capi.h declares, the
+host-side logic of the drop-in (config surface, mask generation, parameter inventory / flat layout, weight-pack
+index maps, LR schedule, registry) and the product's refusal to run without a CUDA device."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from animal2vec_b200 import config as Cfg
+from animal2vec_b200 import lib, masking
+from animal2vec_b200 import params as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not os.path.exists(lib.LIB_PATH):
+        lib.build()
+    return lib.load()
+
+
+def test_library_exports_every_declared_symbol(built):
+    syms = lib.exported_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(built, s), f"liba2v_sm100.so does not export {s}"
+    assert built.a2v_version() >= 1
+
+
+def test_header_cites_reference_lines():
+    txt = open(os.path.join(ROOT, "include", "a2v_capi.h")).read()
+    # every entry-point family names the reference call site it replaces
+    assert len(re.findall(r"nn/[a-z_/0-9]+\.py:\d+", txt)) >= 15
+
+
+def test_no_cpu_path():
+    from animal2vec_b200 import ops
+
+    with pytest.raises(lib.A2VError):
+        ops.colsum(torch.zeros(8, 8), torch.zeros(8))  # CPU tensors are refused, there is no fallback
+    if not torch.cuda.is_available():
+        from animal2vec_b200.engine import PretrainEngine
+
+        with pytest.raises(Exception):
+            PretrainEngine(Cfg.tiny(), "cuda")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "animal2vec_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in re.sub(r'""".*?"""', "", src, flags=re.S).replace("# oracle", ""), fn
+
+
+# ------------------------------------------------------------------------------------------ masks
+def test_masks_bit_exact_against_reference_fixture():
+    g = np.load(os.path.join(GOLD, "masks_large.npz"))
+    m, t, seed, nb = [int(v) for v in g["meta"]]
+    for u in g["updates"]:
+        ref = np.unpackbits(g[f"mask_u{int(u)}"], axis=1)[:, :t].astype(bool)
+        got = masking.pretrain_mask(seed=seed, update=int(u), ids=g["ids"], batch=nb, frames=t, clone_batch=m,
+                                    mask_prob=1.5, mask_length=2)
+        assert np.array_equal(got, ref)
+        assert len(set(got.sum(1).tolist())) == 1  # require_same_masks
+        assert 0.92 < got.mean() < 0.94            # yaml comment: ~93 % masked
+
+
+@pytest.mark.parametrize("name", ["tiny_u0.npz", "tiny_u7_mixup.npz"])
+def test_masks_match_the_step_fixtures(name):
+    g = np.load(os.path.join(GOLD, name))
+    t = int(g["T"])
+    ref = np.unpackbits(g["mask_packed"], axis=1)[:, :t].astype(bool)
+    got = masking.pretrain_mask(seed=1, update=int(g["num_updates"]), ids=list(range(int(g["b"]))), batch=int(g["b"]),
+                                frames=t, clone_batch=3, mask_prob=1.5, mask_length=2)
+    assert np.array_equal(got, ref)
+
+
+def test_mask_edge_cases():
+    # unseeded masks (id=None in the reference's real training runs) still equalise the rows
+    m = masking.pretrain_mask(seed=1, update=0, ids=None, batch=2, frames=100, clone_batch=2, mask_prob=0.5, mask_length=5)
+    assert m.shape == (4, 100) and len(set(m.sum(1).tolist())) == 1
+    # the whole sequence may not be masked
+    with pytest.raises(ValueError):
+        masking.compute_mask_indices(1, 8, 8.0, 2, seed=1, epoch=0, indices=np.array([0]), min_masks=1)
+    # prefetcher returns the same masks as the inline call
+    pf = masking.MaskPrefetcher(seed=3, batch=2, frames=400, clone_batch=3, mask_prob=1.5, mask_length=2)
+    pf.announce(5, [7, 9])
+    a = pf.get(5, [7, 9])
+    b = masking.pretrain_mask(seed=3, update=5, ids=[7, 9], batch=2, frames=400, clone_batch=3, mask_prob=1.5,
+                              mask_length=2)
+    assert np.array_equal(a, b)
+    assert np.array_equal(pf.get(6, [7, 9]), masking.pretrain_mask(seed=3, update=6, ids=[7, 9], batch=2, frames=400,
+                                                                   clone_batch=3, mask_prob=1.5, mask_length=2))
+    pf.close()
+
+
+def test_hash_probes():
+    # SURVEY.md Appendix A (Python 3.12 tuple hashing)
+    assert int(hash((1, 7, 0)) % 1e6) == 697984
+    assert masking.clone_seed_ids(1, np.array([0]), 4).tolist() == [0, 7385056256, 2121911296, 4514358272]
+
+
+# ------------------------------------------------------------------------------------------ config / params
+def test_config_surface_and_counts():
+    c = Cfg.shipped_large()
+    assert (c.embed_dim, c.num_heads, c.depth, c.clone_batch, c.average_top_k_layers) == (1024, 16, 16, 12, 16)
+    a = c.modalities.audio
+    assert (a.prenet_depth, a.conv_pos_depth, a.conv_pos_groups, a.mask_prob, a.mask_length) == (8, 5, 16, 1.5, 2)
+    assert a.num_alibi_heads == 16 and a.model_depth == 16 and a.sample_rate == 8000  # II(...) resolution
+    assert Cfg.parse_conv_layers(a.conv_feature_layers) == [(127, 63, 1), (512, 10, 5)] + [(512, 3, 2)] * 3 + \
+        [(512, 3, 1)] + [(512, 2, 1)] * 2
+    with pytest.raises(ValueError):
+        Cfg.parse_conv_layers("__import__('os').system('true')")
+    shapes = P.student_param_shapes(c)
+    total = sum(int(np.prod(s)) for s in shapes.values())
+    teacher = sum(int(np.prod(s)) for k, s in shapes.items() if P.is_teacher_key(k))
+    assert total == 315_830_026 and teacher == 308_542_480  # SURVEY.md Appendix A [probe]
+    nodecay = [k for k, s in shapes.items() if P.no_decay(k, s)]
+    assert len(shapes) == 342 and len(nodecay) == 226
+    assert sum(int(np.prod(shapes[k])) for k in nodecay) == 340_492
+    # dataclass defaults are the reference's (nn/data2vec2.py:56-166)
+    d = Cfg.Data2VecMultiConfig()
+    assert (d.depth, d.embed_dim, d.num_heads, d.ema_decay, d.ema_end_decay, d.clone_batch) == (8, 768, 12, 0.999, 0.9999, 1)
+    c2 = Cfg.from_dict(Cfg.Data2VecMultiConfig, {"depth": 4, "modalities": {"audio": {"prenet_depth": 2,
+                       "decoder": {"decoder_dim": 96}}}})
+    assert c2.depth == 4 and c2.modalities.audio.prenet_depth == 2 and c2.modalities.audio.decoder.decoder_dim == 96
+
+
+def test_state_dict_keys_match_reference_fixture():
+    g = np.load(os.path.join(GOLD, "tiny_u0.npz"))
+    shapes = P.student_param_shapes(Cfg.tiny())
+    assert set(str(k) for k in g["grad_keys"]) == set(shapes.keys())
+    assert set(str(k) for k in g["ema_keys"]) == set(k for k in shapes if P.is_teacher_key(k))
+
+
+def test_flat_layout_and_pack_maps():
+    cfg = Cfg.tiny()
+    shapes, order, shared = P.student_layout(cfg)
+    fp = P.FlatParams(shapes, "cpu", with_grad=True, order=order)
+    assert order[: len(shared)] == shared and all(o % P.ALIGN == 0 for o in fp.offsets.values())
+    lo, hi = fp.range_of(shared)
+    assert lo == 0 and hi == sum((int(np.prod(shapes[k])) + 7) // 8 * 8 for k in shared)
+
+    def apply(pk, w):
+        out = torch.zeros(int(np.prod(pk.out_shape)))
+        flat = w.reshape(-1)
+        for idx in np.ndindex(*pk.dims):
+            src = pk.in_off + sum(i * s for i, s in zip(idx, pk.in_strides))
+            dst = sum(i * s for i, s in zip(idx, pk.out_strides))
+            out[dst] = flat[src]
+        return out.view(pk.out_shape)
+
+    g_, ng, cg, k = 2, 3, 4, 5
+    w = torch.randn(g_ * ng, cg, k)
+    f = apply(P.pack_conv_fwd("w", g_, ng, cg, k, ngp=4, cgp=8), w)      # (G*ngp, k*cgp)
+    d = apply(P.pack_conv_dgrad("w", g_, ng, cg, k, ngp=4, cgp=8), w)    # (G*cgp, k*ngp)
+    for g0 in range(g_):
+        for n in range(ng):
+            for c in range(cg):
+                for j in range(k):
+                    assert f[g0 * 4 + n, j * 8 + c] == w[g0 * ng + n, c, j]
+                    assert d[g0 * 8 + c, (k - 1 - j) * 4 + n] == w[g0 * ng + n, c, j]
+    assert f.abs().sum() == pytest.approx(w.abs().sum().item(), rel=1e-6)  # pads stay zero
+    lt = apply(P.pack_linear_t("w", 6, 4), torch.arange(24.0).view(6, 4))
+    assert torch.equal(lt, torch.arange(24.0).view(6, 4).t())
+    ct = apply(P.pack_col_t("w", 6, cg, k, 8), torch.randn(6, cg, k))
+    assert ct.shape == (k * 8, 6)
+
+
+def test_lr_schedule_and_decay():
+    from animal2vec_b200.engine import alibi_slopes, annealed_decay
+    from animal2vec_b200.trainer import OptimConfig, cosine_lr
+
+    o = OptimConfig(lr=1e-4, warmup_updates=10, max_update=110)
+    assert cosine_lr(o, 0) == 0.0 and cosine_lr(o, 5) == pytest.approx(5e-5) and cosine_lr(o, 10) == pytest.approx(1e-4)
+    assert cosine_lr(o, 60) == pytest.approx(5e-5) and cosine_lr(o, 110) == pytest.approx(0.0, abs=1e-12)
+    c = Cfg.shipped_large()
+    assert annealed_decay(c, 0) == pytest.approx(0.9997) and annealed_decay(c, 300000) == 1.0
+    assert annealed_decay(c, 150000) == pytest.approx(0.99985)
+    assert np.allclose(alibi_slopes(16), [2 ** (-0.5 * (h + 1)) for h in range(16)])
+    s12 = alibi_slopes(12)
+    assert np.allclose(s12[:8], [2.0 ** -(i + 1) for i in range(8)])
+    assert np.allclose(s12[8:], [2 ** -0.5, 2 ** -1.5, 2 ** -2.5, 2 ** -3.5])
+
+
+def test_registry_names():
+    import animal2vec_b200.criterions  # noqa: F401
+    import animal2vec_b200.data2vec2  # noqa: F401
+    from animal2vec_b200 import registry
+
+    assert "data2vec_multi" in registry.MODELS and "expanded_model" in registry.CRITERIA
+    assert registry.DATACLASSES["data2vec_multi"] is Cfg.Data2VecMultiConfig
+
+
+def test_unsupported_variants_fail_loudly():
+    from animal2vec_b200.engine import PretrainEngine
+
+    c = Cfg.shipped_large()
+    c.layer_norm_first = True
+    with pytest.raises(NotImplementedError):
+        PretrainEngine._check_supported(c)
+    c = Cfg.shipped_large()
+    c.modalities.audio.sinc_norm = "pcen"
+    with pytest.raises(NotImplementedError):
+        PretrainEngine._check_supported(c)
+    PretrainEngine._check_supported(Cfg.shipped_large())  # the shipped recipe itself is supported
