@@ -64,18 +64,45 @@ constexpr int ATT_SMEM_V = 16384 * 3;         // 2 buffers
 constexpr int ATT_SMEM_P = 16384 * 5;         // 2 chunks of 64 keys
 constexpr int ATT_SMEM_POS = 16384 * 7;       // 2 x 128 ints
 constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 1024;
-constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 64 + 1024;
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128 + 1024;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximum may lag by up to 2^8
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Flash-style forward. One thread per query row; per 128-key tile:
+//   S = Q K^T (tcgen05, TMEM)  ->  ONE TMEM read into registers, ALiBi + running max in log2 units
+//   ->  P = exp2(S - m) as bf16 into swizzled smem  ->  O += P V accumulated IN TMEM (tcgen05).
+// O is rescaled in TMEM only when a row's maximum grows by more than 2^8 (lazy rescaling), the S MMA of
+// the next tile is issued before the softmax of this one finishes, K and V tiles have separate
+// barriers so the next K can land while V is still being consumed.
+template <bool HAS_POS, bool DROP>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
     uint64_t* bar_q = bars;
-    uint64_t* bar_kv = bars + 1;  // [2]
-    uint64_t* bar_s = bars + 3;
-    uint64_t* bar_o = bars + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    uint64_t* bar_k = bars + 1;  // [2]
+    uint64_t* bar_v = bars + 3;  // [2]
+    uint64_t* bar_s = bars + 5;
+    uint64_t* bar_o = bars + 6;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
     int* spos = reinterpret_cast<int*>(smem + ATT_SMEM_POS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -85,11 +112,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
 
     if (tid == 0) {
         tma_prefetch_desc(&tm);
-        mbar_init(bar_q, 1);
-        mbar_init(&bar_kv[0], 1);
-        mbar_init(&bar_kv[1], 1);
-        mbar_init(bar_s, 1);
-        mbar_init(bar_o, 1);
+        for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
         mbar_fence_init();
         fence_proxy_async();
     }
@@ -101,144 +124,179 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const uint32_t tmem_s = tmem_base;        // 128 columns
     const uint32_t tmem_o = tmem_base + 128;  // 64 columns
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+    const uint32_t qa = smem_u32(smem + ATT_SMEM_Q);
+
+    auto issue_s = [&](int buf) {
+        const uint32_t ka = smem_u32(smem + ATT_SMEM_K + buf * 16384);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tmem_s, umma_smem_desc(qa + k * 32, 0, 1024), umma_smem_desc(ka + k * 32, 0, 1024), idesc_s,
+                      k > 0 ? 1u : 0u);
+        umma_commit(bar_s);
+    };
 
     if (tid == 0) {
         mbar_expect_tx(bar_q, 16384);
         tma_load_3d(smem + ATT_SMEM_Q, &tm, bar_q, h * HD, q0, b);
-        mbar_expect_tx(&bar_kv[0], 32768);
-        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_kv[0], D + h * HD, 0, b);
-        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_kv[0], 2 * D + h * HD, 0, b);
+        mbar_expect_tx(&bar_k[0], 16384);
+        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_k[0], D + h * HD, 0, b);
+        mbar_expect_tx(&bar_v[0], 16384);
+        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_v[0], 2 * D + h * HD, 0, b);
+        if (n_kv > 1) {
+            mbar_expect_tx(&bar_k[1], 16384);
+            tma_load_3d(smem + ATT_SMEM_K + 16384, &tm, &bar_k[1], D + h * HD, 128, b);
+        }
+        mbar_wait(bar_q, 0);
+        mbar_wait(&bar_k[0], 0);
+        tc_fence_after();
+        issue_s(0);
     }
 
     const int qi = q0 + tid;  // this thread's query row
     const bool q_ok = qi < L;
-    const int pos_i = q_ok ? (p.pos != nullptr ? p.pos[(long long)b * L + qi] : qi) : 0;
+    const int pos_i = q_ok ? (HAS_POS ? p.pos[(long long)b * L + qi] : qi) : 0;
     const float coef2 = head_coef(p, h) * LOG2E;
     const float scale2 = p.sm_scale * LOG2E;
-    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+    const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const long long bh = (long long)b * p.H + h;
 
     float m_run = -INFINITY, l_run = 0.f;
-    float o_acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
-
-    const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-    const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
 
     for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1;
         const int k0 = j * 128;
-        {
+        const bool last = (j == n_kv - 1);
+        if (HAS_POS) {
             const int kj = k0 + tid;
-            spos[buf * 128 + tid] = kj < L ? (p.pos != nullptr ? p.pos[(long long)b * L + kj] : kj) : -(1 << 28);
+            spos[buf * 128 + tid] = kj < L ? p.pos[(long long)b * L + kj] : -(1 << 28);
+            __syncthreads();
         }
-        if (tid == 0) {
-            if (j + 1 < n_kv) {
-                mbar_expect_tx(&bar_kv[buf ^ 1], 32768);
-                tma_load_3d(smem + ATT_SMEM_K + (buf ^ 1) * 16384, &tm, &bar_kv[buf ^ 1], D + h * HD, k0 + 128, b);
-                tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_kv[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
-            }
-            if (j == 0) mbar_wait(bar_q, 0);
-            mbar_wait(&bar_kv[buf], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(smem + ATT_SMEM_Q);
-            const uint32_t ka = smem_u32(smem + ATT_SMEM_K + buf * 16384);
-#pragma unroll
-            for (int k = 0; k < HD / 16; ++k)
-                umma_bf16(tmem_s, umma_smem_desc(qa + k * 32, 0, 1024), umma_smem_desc(ka + k * 32, 0, 1024), idesc_s,
-                          k > 0 ? 1u : 0u);
-            umma_commit(bar_s);
-        }
-        __syncthreads();  // spos visible
         mbar_wait(bar_s, j & 1);
         tc_fence_after();
+        if (tid == 0 && j + 2 < n_kv) {  // K buffer `buf` is free: S(j) has been computed
+            mbar_expect_tx(&bar_k[buf], 16384);
+            tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
+        }
 
-        // pass 1: row maximum
+        // scores -> registers (log2 units, ALiBi added), row maximum
+        float t[128];
         float m_tile = -INFINITY;
-#pragma unroll 1
+        const float dist0 = (float)(pos_i - k0);
+        const int nvalid = L - k0;  // keys of this tile that exist (>= 128 except for the last tile)
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint32_t raw[32];
             tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int pk = spos[buf * 128 + c * 32 + i];
-                const float t = __uint_as_float(raw[i]) * scale2 - coef2 * fabsf((float)(pos_i - pk));
-                m_tile = fmaxf(m_tile, pk >= 0 ? t : -INFINITY);
+                const int col = c * 32 + i;
+                float dist;
+                if (HAS_POS) dist = (float)(pos_i - spos[buf * 128 + col]);
+                else dist = dist0 - (float)col;
+                float v = fmaf(__uint_as_float(raw[i]), scale2, -coef2 * fabsf(dist));
+                if (last && col >= nvalid) v = -INFINITY;
+                t[col] = v;
+                m_tile = fmaxf(m_tile, v);
             }
         }
-        const float m_new = fmaxf(m_run, m_tile);
-        const float alpha = exp2f(m_run - m_new);  // first tile: exp2(-inf) = 0
-        float l_tile = 0.f;
-        // pass 2: probabilities -> shared memory (bf16, 128B-swizzled K-major A operand)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
-            tmem_ld_wait();
-            float pv[32];
+        // previous P.V done: P smem, V[buf^1] and the O accumulator are ours again
+        if (j > 0) {
+            mbar_wait(bar_o, (j - 1) & 1);
+            tc_fence_after();
+        }
+        if (tid == 0 && j + 1 < n_kv) {
+            mbar_expect_tx(&bar_v[buf ^ 1], 16384);
+            tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
+        }
+        // lazy rescaling of O (in TMEM) and of the running sum
+        const bool grow = m_tile > m_run + ATT_RESCALE_THRESHOLD;  // also true on the first tile (m_run = -inf)
+        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+            const float alpha = grow ? ex2_approx(m_run - m_tile) : 1.0f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int pk = spos[buf * 128 + c * 32 + i];
-                const float t = __uint_as_float(raw[i]) * scale2 - coef2 * fabsf((float)(pos_i - pk));
-                float e = pk >= 0 ? exp2f(t - m_new) : 0.f;
-                l_tile += e;
-                if (p.drop_p > 0.f) e = attn_keep(p.seed, bh, L, qi, k0 + c * 32 + i, p.drop_p) ? e * inv_keep : 0.f;
-                pv[i] = e;
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_o + lane_off + c * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+                tmem_st_32x32(tmem_o + lane_off + c * 32, raw);
             }
-            // chunk c covers keys c*32..c*32+31 = 64-key half (c>>1), 16-byte units ((c&1)*4 .. +3)
+            tmem_st_wait();
+            l_run *= alpha;
+        }
+        if (grow) m_run = m_tile;
+
+        // probabilities -> shared memory (bf16, 128B-swizzled K-major A operand of P.V)
+        float l_tile = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
             uint8_t* prow = smem + ATT_SMEM_P + (c >> 1) * 16384 + tid * 128;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                float e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = ex2_approx(t[c * 32 + u * 8 + i] - m_run);
+                    l_tile += e[i];
+                }
+                if (DROP) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        e[i] = attn_keep(p.seed, bh, L, qi, k0 + c * 32 + u * 8 + i, p.drop_p) ? e[i] * inv_keep : 0.f;
+                }
                 uint4 v;
-                v.x = pack_bf16x2(pv[8 * u + 0], pv[8 * u + 1]);
-                v.y = pack_bf16x2(pv[8 * u + 2], pv[8 * u + 3]);
-                v.z = pack_bf16x2(pv[8 * u + 4], pv[8 * u + 5]);
-                v.w = pack_bf16x2(pv[8 * u + 6], pv[8 * u + 7]);
+                v.x = pack_bf16x2(e[0], e[1]);
+                v.y = pack_bf16x2(e[2], e[3]);
+                v.z = pack_bf16x2(e[4], e[5]);
+                v.w = pack_bf16x2(e[6], e[7]);
                 const int unit = ((c & 1) * 4 + u) ^ (tid & 7);
                 *reinterpret_cast<uint4*>(prow + unit * 16) = v;
             }
         }
-        l_run = l_run * alpha + l_tile;
-        m_run = m_new;
+        l_run += l_tile;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
+            mbar_wait(&bar_v[buf], (j >> 1) & 1);
             const uint32_t pa = smem_u32(smem + ATT_SMEM_P);
             const uint32_t va = smem_u32(smem + ATT_SMEM_V + buf * 16384);
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 umma_bf16(tmem_o, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                          umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+                          umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
             umma_commit(bar_o);
+            if (j + 1 < n_kv) {  // S of the next tile: every thread has its scores in registers by now
+                mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
+                issue_s(buf ^ 1);
+            }
         }
-#pragma unroll
-        for (int d = 0; d < HD; ++d) o_acc[d] *= alpha;
-        mbar_wait(bar_o, j & 1);
-        tc_fence_after();
+    }
+
+    mbar_wait(bar_o, (n_kv - 1) & 1);
+    tc_fence_after();
+    {
+        const float inv_l = 1.0f / l_run;
+        bf16* orow = reinterpret_cast<bf16*>(p.out) + ((long long)b * L + qi) * D + h * HD;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             uint32_t raw[32];
             tmem_ld_32x32(tmem_o + lane_off + c * 32, raw);
             tmem_ld_wait();
+            if (q_ok) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(raw[i]);
+                for (int d = 0; d < 32; d += 4) {
+                    float v[4] = {__uint_as_float(raw[d]) * inv_l, __uint_as_float(raw[d + 1]) * inv_l,
+                                  __uint_as_float(raw[d + 2]) * inv_l, __uint_as_float(raw[d + 3]) * inv_l};
+                    store4(orow + c * 32 + d, v);
+                }
+            }
         }
-        tc_fence_before();
-    }
-
-    if (q_ok) {
-        const float inv_l = 1.0f / l_run;
-        bf16* orow = reinterpret_cast<bf16*>(p.out) + ((long long)b * L + qi) * D + h * HD;
-#pragma unroll
-        for (int d = 0; d < HD; d += 4) {
-            float v[4] = {o_acc[d] * inv_l, o_acc[d + 1] * inv_l, o_acc[d + 2] * inv_l, o_acc[d + 3] * inv_l};
-            store4(orow + d, v);
-        }
-        if (p.lse != nullptr) p.lse[bh * L + qi] = (m_run + log2f(l_run)) * LN2;
+        if (q_ok && p.lse != nullptr) p.lse[bh * L + qi] = (m_run + log2f(l_run)) * LN2;
     }
     tc_fence_before();
     __syncthreads();
@@ -586,15 +644,24 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     }
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             ATT_SMEM_TOTAL);
+        cudaError_t e = cudaSuccess;
+#define A2V_ATT_CFG(P_, D_)                                                                                   \
+    if (e == cudaSuccess)                                                                                     \
+        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 ATT_SMEM_TOTAL);
+        A2V_ATT_CFG(false, false) A2V_ATT_CFG(false, true) A2V_ATT_CFG(true, false) A2V_ATT_CFG(true, true)
+#undef A2V_ATT_CFG
         if (e != cudaSuccess) {
             a2v_set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
             return A2V_ERR_CUDA;
         }
         configured = true;
     }
-    attn_fwd_tcgen05_kernel<<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    const bool has_pos = p.pos != nullptr, drop = p.drop_p > 0.f;
+    if (has_pos && drop) attn_fwd_tcgen05_kernel<true, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    else if (has_pos) attn_fwd_tcgen05_kernel<true, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    else if (drop) attn_fwd_tcgen05_kernel<false, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    else attn_fwd_tcgen05_kernel<false, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
     return a2v_check_launch("attn_fwd_tcgen05");
 }
 
