@@ -25,7 +25,7 @@ struct GemmParams {
     int M, N;
     int kb_per_tap, taps, batch, groups;
     int m_tiles, n_tiles;
-    int a_group_stride, a_row_off, a_tap_rows;
+    int a_group_stride, a_row_off, a_tap_rows, a_tap_cols;
     int b_group_stride, b_row_off, b_tap_rows;
     int red_rows, kb_per_batch, k_splits;
     void* c;
@@ -274,9 +274,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const int b = kb / p.kb_per_batch;
                         const int r0 = (kb - b * p.kb_per_batch) * BLOCK_K;
 #pragma unroll
-                        for (int i = 0; i < BLOCK_M / 64; ++i)
+                        for (int i = 0; i < BLOCK_M / 64; ++i) {
+                            // a_tap_cols > 0: the M index is (tap, channel); every 64-column box of A reads
+                            // rows shifted by its own tap (weight gradient of a stride-1 conv, x as the M side)
+                            const int m0 = t.m_tile * BLOCK_M + i * 64;
+                            const int tap = p.a_tap_cols > 0 ? m0 / p.a_tap_cols : 0;
+                            const int c0 = m0 - tap * p.a_tap_cols;
                             tma_load_3d(sa + i * (64 * BLOCK_K * 2), &tmA, &full_bar[stage],
-                                        t.g * p.a_group_stride + t.m_tile * BLOCK_M + i * 64, r0, b);
+                                        t.g * p.a_group_stride + c0,
+                                        r0 + (p.a_tap_cols > 0 ? tap * p.a_tap_rows + p.a_row_off : 0), b);
+                        }
 #pragma unroll
                         for (int i = 0; i < BLOCK_N / 64; ++i)
                             tma_load_3d(sb + i * (64 * BLOCK_K * 2), &tmB, &full_bar[stage],
@@ -520,6 +527,7 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
     p.a_group_stride = d->a_group_stride;
     p.a_row_off = d->a_row_off;
     p.a_tap_rows = d->a_tap_rows;
+    p.a_tap_cols = d->a_tap_cols;
     p.b_group_stride = d->b_group_stride;
     p.b_row_off = d->b_row_off;
     p.b_tap_rows = d->b_tap_rows;
@@ -550,10 +558,13 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         p.num_tiles = p.n_tiles * p.m_tiles * p.batch * p.groups;
         if ((rc = make_map(&ta, d->a, BLOCK_M, "A")) != A2V_OK) return rc;
         if ((rc = make_map(&tb, d->b, d->block_n, "B")) != A2V_OK) return rc;
+        A2V_REQUIRE(d->a_tap_cols == 0, "gemm: a_tap_cols is a TN-mode field");
     } else {
         A2V_REQUIRE(d->red_rows > 0 && d->k_splits >= 1, "gemm: TN mode needs red_rows > 0 and k_splits >= 1");
         A2V_REQUIRE(d->k_splits == 1 || d->out_atomic, "gemm: split-K requires out_atomic");
         A2V_REQUIRE(d->bias == nullptr, "gemm: TN mode has no bias epilogue");
+        A2V_REQUIRE(d->a_tap_cols == 0 || (d->a_tap_cols > 0 && d->a_tap_cols % 64 == 0 && d->taps == 1),
+                    "gemm: a_tap_cols must be a multiple of 64 (and taps == 1: the taps live in M)");
         p.red_rows = d->red_rows;
         p.kb_per_batch = ceil_div(d->red_rows, BLOCK_K);
         p.k_splits = d->k_splits;

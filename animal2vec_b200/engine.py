@@ -251,10 +251,20 @@ class PretrainEngine:
         sp[n + "|T"] = P.pack_cols_padded_t(n, d, dg, self.dec_ng, GP)
         self.sp, self.tp = sp, tp
         # packed fp32 gradient buffers for weights whose GEMM layout differs from the checkpoint layout
+        # (tap convs: TRANSPOSED layout (G*k*Cg, Ng) written by gemm.conv_wgrad_tn, see params.pack_conv_fwd)
         self.gpacked: Dict[str, torch.Tensor] = {}
+        self.gt_keys = set()
+        for i, (_c, _k, st) in enumerate(self.layers[1:], start=1):
+            if st == 1:
+                self.gt_keys.add(le + f"{i}.0.weight|F")
+        for n in self.pos_names:
+            self.gt_keys.add(n + "|F")
+        for l in range(dc.decoder_layers):
+            self.gt_keys.add(ENC + f"decoder.blocks.{l}.0.weight|F")
         for key, pk in sp.items():
             if key.endswith("|F") or key.endswith("|B"):
-                self.gpacked[key] = torch.zeros(pk.out_shape, device=self.device, dtype=torch.float32)
+                shape = pk.gt_shape if key in self.gt_keys else pk.out_shape
+                self.gpacked[key] = torch.zeros(shape, device=self.device, dtype=torch.float32)
         self.WS, self.WT = _Weights(), _Weights()
 
     def _refresh_student(self) -> None:
@@ -736,7 +746,7 @@ class PretrainEngine:
         """Packed-layout weight gradients -> checkpoint-layout views of the flat gradient buffer."""
         for key, buf in self.gpacked.items():
             name, _ = key.split("|")
-            P.unpack_grad(self.sp[key], buf, self.G(name))  # G += packed
+            P.unpack_grad(self.sp[key], buf, self.G(name), transposed=key in self.gt_keys)  # G += packed
             buf.zero_()
 
     def zero_grad(self) -> None:

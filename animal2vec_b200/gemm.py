@@ -225,24 +225,27 @@ def conv_wgrad_tn(
     groups: int = 1,
     k_splits: Optional[int] = None,
 ) -> torch.Tensor:
-    """Weight gradient of :func:`conv_nt`, atomically accumulated into fp32 ``out`` (G*Ng, taps*Cg):
-        out[g*Ng + n, j*Cg + c] += sum_{b, t} dy[b, t, g*Ng + n] * x[b, t + j - pad, g*Cg + c].
+    """Weight gradient of :func:`conv_nt`, atomically accumulated into fp32 ``out`` of shape
+    (G*taps*Cg, Ng) -- TRANSPOSED relative to the forward weight layout so that x (with the taps folded
+    into M, two taps per 128-row MMA tile) is the M side and the tile rows are contiguous in ``out``:
+        out[(g*taps + j)*Cg + c, n] += sum_{b, t} x[b, t + j - pad, g*Cg + c] * dy[b, t, g*Ng + n].
     """
     bsz, t, cin = x.shape
     nout = dy.shape[-1]
     cg, ng = cin // groups, nout // groups
     assert dy.shape[:2] == x.shape[:2] and dy.is_contiguous() and x.is_contiguous()
-    assert out.dtype == torch.float32 and out.shape == (nout, taps * cg) and out.is_contiguous()
+    assert cg % 64 == 0, "conv_wgrad_tn: channels per group must be a multiple of 64"
+    assert out.dtype == torch.float32 and out.shape == (groups * taps * cg, ng) and out.is_contiguous()
     d = L.GemmDesc()
     d.mode = 1
-    d.block_n = 64 if cg <= 64 else (128 if cg <= 128 else 256)
-    d.a = _operand(dy, nout, t, bsz, nout, t * nout)
-    d.b = _operand(x, cin, t, bsz, cin, t * cin)
-    d.M, d.N, d.taps, d.batch, d.groups = ng, cg, taps, bsz, groups
-    d.a_group_stride = ng
-    d.b_group_stride, d.b_row_off, d.b_tap_rows = cg, -pad, 1
+    d.block_n = 64 if ng <= 64 else (128 if ng <= 128 else 256)
+    d.a = _operand(x, cin, t, bsz, cin, t * cin)
+    d.b = _operand(dy, nout, t, bsz, nout, t * nout)
+    d.M, d.N, d.taps, d.batch, d.groups = taps * cg, ng, 1, bsz, groups
+    d.a_group_stride, d.a_row_off, d.a_tap_rows, d.a_tap_cols = cg, -pad, 1, cg
+    d.b_group_stride, d.b_row_off, d.b_tap_rows = ng, 0, 0
     d.red_rows = t
-    tiles = -(-ng // 128) * -(-cg // d.block_n) * taps * groups
+    tiles = -(-(taps * cg) // 128) * -(-ng // d.block_n) * groups
     kblocks = bsz * -(-t // 64)
     ks = k_splits or _pick_splits(tiles, kblocks)
     per = -(-kblocks // ks)
@@ -250,9 +253,9 @@ def conv_wgrad_tn(
     d.c = out.data_ptr()
     d.c_dtype = L.F32
     d.out_atomic = 1
-    d.ldc = taps * cg
-    d.c_group_stride = ng
-    d.c_tap_stride = cg
+    d.ldc = ng
+    d.c_group_stride = taps * cg
+    d.c_tap_stride = 0
     d.alpha = 1.0
     _launch(d, x)
     return out

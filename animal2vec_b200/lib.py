@@ -85,6 +85,7 @@ class GemmDesc(C.Structure):
         ("preact", C.c_void_p),
         ("residual", C.c_void_p),
         ("dgelu_u", C.c_void_p),
+        ("a_tap_cols", C.c_int),
     ]
 
 

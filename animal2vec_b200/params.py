@@ -146,7 +146,8 @@ class Pack:
     """A GEMM-operand view of one parameter: 4-D index map from the reference layout into a dense,
     possibly padded buffer. ``split_k`` is the K granularity of the fp32-mode hi/lo split."""
 
-    __slots__ = ("src", "dims", "in_strides", "in_off", "out_strides", "out_shape", "split_k", "buf", "fbuf", "is_bias")
+    __slots__ = ("src", "dims", "in_strides", "in_off", "out_strides", "out_shape", "split_k", "buf", "fbuf", "is_bias",
+                 "gt_strides", "gt_shape")
 
     def __init__(self, src, dims, in_strides, in_off, out_strides, out_shape, split_k, is_bias=False):
         self.src, self.dims, self.in_strides, self.in_off = src, list(dims), list(in_strides), in_off
@@ -154,6 +155,8 @@ class Pack:
         self.buf = None
         self.fbuf = None
         self.is_bias = is_bias
+        self.gt_strides = None  # strides of the same 4-D index space in the TRANSPOSED conv weight-gradient buffer
+        self.gt_shape = None
 
 
 def pack_linear_t(name, n_out, k_in) -> Pack:
@@ -164,8 +167,12 @@ def pack_linear_t(name, n_out, k_in) -> Pack:
 def pack_conv_fwd(name, groups, ng, cg, k, ngp=None, cgp=None) -> Pack:
     """torch Conv1d weight (G*ng, cg, k) -> (G*ngp, k*cgp), tap-major, channel-minor, zero padded."""
     ngp, cgp = ngp or ng, cgp or cg
-    return Pack(name, (groups, ng, k, cg), (ng * cg * k, cg * k, 1, k), 0, (ngp * k * cgp, k * cgp, cgp, 1),
-                (groups * ngp, k * cgp), cgp)
+    pk = Pack(name, (groups, ng, k, cg), (ng * cg * k, cg * k, 1, k), 0, (ngp * k * cgp, k * cgp, cgp, 1),
+              (groups * ngp, k * cgp), cgp)
+    # gemm.conv_wgrad_tn writes (G*k*cgp, ngp): element (g, n, j, c) at ((g*k + j)*cgp + c)*ngp + n
+    pk.gt_strides = [k * cgp * ngp, 1, cgp * ngp, ngp]
+    pk.gt_shape = (groups * k * cgp, ngp)
+    return pk
 
 
 def pack_conv_dgrad(name, groups, ng, cg, k, ngp=None, cgp=None) -> Pack:
@@ -217,10 +224,11 @@ def materialize(p: Pack, src: torch.Tensor, fp32_mode: bool) -> torch.Tensor:
     return p.buf
 
 
-def unpack_grad(p: Pack, packed_grad: torch.Tensor, dst: torch.Tensor) -> None:
+def unpack_grad(p: Pack, packed_grad: torch.Tensor, dst: torch.Tensor, transposed: bool = False) -> None:
     """Inverse index map: ADD the packed-layout fp32 gradient into the reference-layout view (the packed
     buffers are transient per backward; the flat gradient buffer is the only accumulator)."""
-    ops.relayout(packed_grad, dst, p.dims, p.out_strides, 0, p.in_strides, p.in_off, accumulate=True)
+    strides = p.gt_strides if transposed else p.out_strides
+    ops.relayout(packed_grad, dst, p.dims, strides, 0, p.in_strides, p.in_off, accumulate=True)
 
 
 # --------------------------------------------------------------------------------------------

@@ -94,6 +94,9 @@ typedef struct {
     void* preact;          /* optional: pre-activation copy, same layout/dtype as C */
     const void* residual;  /* optional: added after the activation, same layout/dtype as C */
     const void* dgelu_u;   /* optional: result *= GELU'(u), same layout/dtype as C */
+    int a_tap_cols;        /* TN only, 0 = off: M index = tap * a_tap_cols + channel; the A box of tap j reads
+                              rows shifted by a_row_off + j * a_tap_rows (conv weight gradient with x as the
+                              M side: C[(j, c), n] = sum_t x[t + j - pad, c] * dy[t, n]) */
 } a2v_gemm_desc;
 
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);

@@ -87,7 +87,8 @@ def test_gemm_tn(r, m, n, bn, ks):
     assert _rel(out, 2 * ref) < 1e-5
 
 
-@pytest.mark.parametrize("bsz,t,cg,ng,groups,taps", [(2, 300, 64, 64, 4, 19), (3, 130, 64, 64, 2, 7), (2, 257, 128, 128, 1, 3)])
+@pytest.mark.parametrize("bsz,t,cg,ng,groups,taps", [(2, 300, 64, 64, 4, 19), (3, 130, 64, 64, 2, 7), (2, 257, 128, 128, 1, 3),
+                                                    (2, 200, 512, 512, 1, 3), (1, 333, 128, 320, 1, 3)])
 def test_conv_wgrad_tn(bsz, t, cg, ng, groups, taps):
     from animal2vec_b200 import gemm
 
@@ -98,7 +99,8 @@ def test_conv_wgrad_tn(bsz, t, cg, ng, groups, taps):
     wt = torch.zeros(groups * ng, cg, taps, device="cuda", requires_grad=True)
     y = F.conv1d(xt, wt, None, padding=pad, groups=groups)
     y.backward(dy.float().transpose(1, 2))
-    ref = wt.grad.permute(0, 2, 1).reshape(groups * ng, taps * cg)
-    out = torch.zeros(groups * ng, taps * cg, device="cuda")
+    # transposed layout: out[(g*taps + j)*cg + c, n] = dW[g*ng + n, c, j]
+    ref = wt.grad.view(groups, ng, cg, taps).permute(0, 3, 2, 1).reshape(groups * taps * cg, ng)
+    out = torch.zeros(groups * taps * cg, ng, device="cuda")
     gemm.conv_wgrad_tn(dy, x, out, taps=taps, pad=pad, groups=groups)
     assert _rel(out, ref) < 1e-5, _rel(out, ref)

@@ -48,7 +48,7 @@ def main():
     fl = 2 * 24 * 2000 * 1024 * 64 * 19
     res.append({"op": "conv_nt", "ms": ms, "tflops": fl / ms / 1e9})
     print(res[-1], flush=True)
-    dw = torch.zeros(1024, 19 * 64, device="cuda")
+    dw = torch.zeros(16 * 19 * 64, 64, device="cuda")
     ms = bench(lambda: gemm.conv_wgrad_tn(x, x, dw, taps=19, pad=9, groups=16))
     res.append({"op": "conv_wgrad_tn", "ms": ms, "tflops": fl / ms / 1e9})
     print(res[-1], flush=True)
