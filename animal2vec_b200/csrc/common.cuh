@@ -83,9 +83,14 @@ __device__ __forceinline__ float gelu_exact_grad(float x) {
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7): one rcp + one ex2 instead of erff's
 // long polynomial. Used by the bf16 kernels (the fp32 validation kernels keep erff).
 //   erf(u) = sign(u) * (1 - poly(t) * exp(-u^2)),  t = 1 / (1 + 0.3275911 |u|)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float gelu_fast(float x) {
     const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
     const float e = __expf(-u * u);
     float pl = fmaf(1.061405429f, t, -1.453152027f);
     pl = fmaf(pl, t, 1.421413741f);
@@ -96,7 +101,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 __device__ __forceinline__ float gelu_fast_grad(float x) {
     const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, u, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
     const float e = __expf(-u * u);                      // = exp(-x^2/2): shared by erf and the pdf
     float pl = fmaf(1.061405429f, t, -1.453152027f);
     pl = fmaf(pl, t, 1.421413741f);

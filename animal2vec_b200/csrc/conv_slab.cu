@@ -1,0 +1,340 @@
+// Grouped stride-1 "tap" convolution with 64-channel groups as a tcgen05 implicit GEMM that loads every
+// activation row ONCE per tile (a row "slab" with the tap halo) instead of once per tap.
+//
+//   y[b, t, g*YG + n] = sum_{j < taps} sum_{c < 64} x[b, t + j - pad, g*64 + c] * w[g*WG + n, j*64 + c]  (+ bias)
+//
+// Replaces the cuDNN grouped Conv1d dispatch of the reference's relative positional encoder
+// (/root/reference/nn/modalities/audio.py:93-113: 5 x Conv1d(D, D, k=19, groups=16)) and of Decoder1d
+// (nn/modalities/modules.py:141-157: Conv1d(k=7, groups=16)), forward and data gradient (the data
+// gradient is the same operator on dy with flipped/transposed weights, see params.pack_conv_dgrad).
+//
+// Why a slab: with one 128x64 A tile per tap (the generic tap loop of gemm_sm100.cu) a 19-tap layer pulls
+// 19 x 16 KB of overlapping rows through L2 per 128x64 output tile (~190 B/clk/SM at the MMA rate): the
+// kernel is L2-bandwidth bound. Here one TMA box brings rows [m0 - pad, m0 - pad + 256 + taps - 1) of
+// the group's 64 channels into a 128B-swizzled slab; the A operand of tap j is the SAME shared memory
+// shifted down by j rows (descriptor start address + j*128 B; the 128B swizzle is a function of the
+// absolute shared-memory address, so the shifted view stays consistent with what TMA wrote). Two 128-row output tiles share each weight tile. Warp roles as in gemm_sm100.cu:
+// warp 0 TMA producer, warp 1 tcgen05.mma issuer (one thread), warps 2..5 epilogue out of
+// double-buffered TMEM accumulators.
+#include <string.h>
+#include "common.cuh"
+#include "../../include/a2v_capi.h"
+
+namespace a2v {
+
+constexpr int CS_BLOCK_M = 128;
+constexpr int CS_MT = 2;                        // 128-row tiles per slab
+constexpr int CS_SUPER_M = CS_BLOCK_M * CS_MT;  // output rows per tile
+constexpr int CS_NB = 6;                        // weight-tile ring stages (8 KB each)
+constexpr int CS_B_BYTES = 64 * 64 * 2;
+constexpr int CS_THREADS = 192;
+constexpr int CS_EPI_PITCH = 36;
+constexpr int CS_EPI_BYTES = 4 * 32 * CS_EPI_PITCH * 4;
+
+struct ConvSlabParams {
+    int batch, T, groups, taps, pad, ng;
+    int w_group_rows, y_group_cols;
+    long long ldy;
+    void* y;
+    int y_f32;
+    const float* bias;
+    int slab_rows;   // multiple of 16, >= CS_SUPER_M + taps - 1
+    int m_tiles;     // ceil(T / CS_SUPER_M)
+    int num_tiles;
+    int bo_mode;
+};
+
+__device__ __forceinline__ uint64_t umma_smem_desc_bo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)(base_off & 7u) << 49;  // matrix base offset: start row inside the 8-row swizzle atom
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+
+template <typename TC>
+__device__ __forceinline__ void cs_store_chunk(const ConvSlabParams& p, const float (&v)[32], long long row_off0,
+                                               int rows_ok, int gcol, int cols_ok, int lane) {
+    const int rsub = lane >> 3;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (j < cols_ok) bias[j] = p.bias[gcol + j];
+    }
+    TC* y = reinterpret_cast<TC*>(p.y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = rsub + 4 * i;
+        if (r >= rows_ok || cols_ok <= 0) continue;
+        float x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = v[4 * i + j] + bias[j];
+        TC* c = y + row_off0 + (long long)r * p.ldy + gcol;
+        if (cols_ok >= 4) {
+            store4(c, x);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (j < cols_ok) c[j] = from_f32<TC>(x[j]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CS_THREADS, 1)
+conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                     const ConvSlabParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int slab_bytes = p.slab_rows * 128;
+    uint8_t* slab0 = smem;
+    uint8_t* bring = smem + 2 * slab_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bring + CS_NB * CS_B_BYTES);
+    uint64_t* slab_full = bars;            // [2]
+    uint64_t* slab_empty = bars + 2;       // [2]
+    uint64_t* b_full = bars + 4;           // [CS_NB]
+    uint64_t* b_empty = b_full + CS_NB;    // [CS_NB]
+    uint64_t* tfull = b_empty + CS_NB;     // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&slab_full[i], 1);
+            mbar_init(&slab_empty[i], 1);
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        for (int i = 0; i < CS_NB; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+        }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (m super tile, batch, group): consecutive tiles share the group's weights (L2 friendly)
+    auto decode = [&](int tile, int& ms, int& b, int& g) {
+        ms = tile % p.m_tiles;
+        tile /= p.m_tiles;
+        b = tile % p.batch;
+        g = tile / p.batch;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ss = 0, bs = 0;
+            uint32_t sphase = 0, bphase = 0;
+            const int half_rows = p.slab_rows >> 1;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int ms, b, g;
+                decode(tile, ms, b, g);
+                mbar_wait(&slab_empty[ss], sphase ^ 1);
+                uint8_t* slab = slab0 + ss * slab_bytes;
+                mbar_expect_tx(&slab_full[ss], (uint32_t)slab_bytes);
+                const int r0 = ms * CS_SUPER_M - p.pad;
+                tma_load_3d(slab, &tmX, &slab_full[ss], g * 64, r0, b);
+                tma_load_3d(slab + half_rows * 128, &tmX, &slab_full[ss], g * 64, r0 + half_rows, b);
+                if (++ss == 2) { ss = 0; sphase ^= 1; }
+                for (int j = 0; j < p.taps; ++j) {
+                    mbar_wait(&b_empty[bs], bphase ^ 1);
+                    mbar_expect_tx(&b_full[bs], CS_B_BYTES);
+                    tma_load_3d(bring + bs * CS_B_BYTES, &tmW, &b_full[bs], j * 64, g * p.w_group_rows, 0);
+                    if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(CS_BLOCK_M, 64, false, false);
+            int ss = 0, bs = 0, as = 0;
+            uint32_t sphase = 0, bphase = 0, aphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[as], aphase ^ 1);
+                mbar_wait(&slab_full[ss], sphase);
+                tc_fence_after();
+                const uint32_t slab = smem_u32(slab0 + ss * slab_bytes);
+                for (int j = 0; j < p.taps; ++j) {
+                    mbar_wait(&b_full[bs], bphase);
+                    tc_fence_after();
+                    const uint32_t wb = smem_u32(bring + bs * CS_B_BYTES);
+                    // measured on B200: the swizzle phase comes from the absolute smem address bits [7:9]; a row-shifted
+                    // start address needs NO base-offset correction (bo_mode 1 is a debugging aid only)
+                    const uint32_t bo = p.bo_mode == 1 ? (uint32_t)(j & 7) : 0u;
+#pragma unroll
+                    for (int mt = 0; mt < CS_MT; ++mt) {
+                        const uint32_t a0 = slab + (uint32_t)(mt * CS_BLOCK_M + j) * 128u;
+                        const uint32_t td = tmem_base + as * (CS_MT * 64) + mt * 64;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(td, umma_smem_desc_bo(a0 + k * 32, 1024, bo), umma_smem_desc(wb + k * 32, 0, 1024),
+                                      idesc, (j > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&b_empty[bs]);
+                    if (++bs == CS_NB) { bs = 0; bphase ^= 1; }
+                }
+                umma_commit(&slab_empty[ss]);
+                umma_commit(&tfull[as]);
+                if (++ss == 2) { ss = 0; sphase ^= 1; }
+                if (++as == 2) { as = 0; aphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        int as = 0;
+        uint32_t aphase = 0;
+        const uint32_t st = smem_u32(epi_stage + (warp - 2) * (32 * CS_EPI_PITCH));
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            int ms, b, g;
+            decode(tile, ms, b, g);
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < CS_MT; ++mt) {
+                const int row0 = ms * CS_SUPER_M + mt * CS_BLOCK_M + q * 32;
+                int rows_ok = p.T - row0;
+                rows_ok = rows_ok > 32 ? 32 : rows_ok;
+                const long long row_off0 = ((long long)b * p.T + row0) * p.ldy;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (CS_MT * 64) + mt * 64 + c * 32, raw);
+                    tmem_ld_wait();
+                    if (c * 32 >= p.ng) break;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (lane * CS_EPI_PITCH + 4 * j) * 4),
+                                     "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
+                                     : "memory");
+                    __syncwarp();
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(v[4 * i]), "=f"(v[4 * i + 1]), "=f"(v[4 * i + 2]), "=f"(v[4 * i + 3])
+                                     : "r"(st + (((lane >> 3) + 4 * i) * CS_EPI_PITCH + (lane & 7) * 4) * 4)
+                                     : "memory");
+                    __syncwarp();
+                    const int lcol = c * 32 + (lane & 7) * 4;
+                    const int cols_ok = p.ng - lcol;
+                    if (rows_ok > 0) {
+                        if (p.y_f32)
+                            cs_store_chunk<float>(p, v, row_off0, rows_ok, g * p.y_group_cols + lcol, cols_ok, lane);
+                        else
+                            cs_store_chunk<bf16>(p, v, row_off0, rows_ok, g * p.y_group_cols + lcol, cols_ok, lane);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn3 cs_encode_fn() {
+    static EncodeTiledFn3 fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn3>(sym);
+    }
+    return fn;
+}
+
+static int cs_make_map(CUtensorMap* m, const void* ptr, long long cols, long long rows, long long batch, long long ld,
+                       int box_rows, const char* name) {
+    EncodeTiledFn3 fn = cs_encode_fn();
+    if (fn == nullptr) {
+        a2v_set_error("conv_slab: cuTensorMapEncodeTiled not available");
+        return A2V_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * rows * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        a2v_set_error("conv_slab: cuTensorMapEncodeTiled(%s) failed with CUresult %d", name, (int)r);
+        return A2V_ERR_CUDA;
+    }
+    return A2V_OK;
+}
+
+}  // namespace a2v
+
+using namespace a2v;
+
+extern "C" int a2v_conv_slab_supported(const a2v_conv_desc* d) {
+    return d != nullptr && d->taps >= 1 && d->taps <= 32 && d->ng >= 1 && d->ng <= 64 && d->ldx % 8 == 0 &&
+           d->x_group_cols == 64 && d->T >= 1 && d->pad >= 0 && d->pad < d->taps;
+}
+
+extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
+    A2V_REQUIRE(d != nullptr && d->x && d->w && d->y, "conv_slab: NULL pointer");
+    A2V_REQUIRE(a2v_conv_slab_supported(d), "conv_slab: needs 64-channel groups, ng <= 64, taps <= 32");
+    A2V_REQUIRE(d->y_dtype == A2V_F32 || d->y_dtype == A2V_BF16, "conv_slab: bad y dtype");
+    A2V_REQUIRE(((uintptr_t)d->x & 15) == 0 && ((uintptr_t)d->w & 15) == 0 && ((uintptr_t)d->y & 15) == 0,
+                "conv_slab: pointers must be 16-byte aligned");
+    const int vec = d->y_dtype == A2V_F32 ? 4 : 8;
+    A2V_REQUIRE(d->ldy % vec == 0 && d->y_group_cols % vec == 0, "conv_slab: ldy / group stride alignment");
+    A2V_REQUIRE(d->ldw % 8 == 0 && d->ldw >= (int64_t)d->taps * 64, "conv_slab: bad weight row stride");
+    ConvSlabParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = d->batch; p.T = d->T; p.groups = d->groups; p.taps = d->taps; p.pad = d->pad; p.ng = d->ng;
+    p.w_group_rows = d->w_group_rows; p.y_group_cols = d->y_group_cols;
+    p.ldy = d->ldy; p.y = d->y; p.y_f32 = d->y_dtype == A2V_F32; p.bias = d->bias;
+    p.slab_rows = (CS_SUPER_M + d->taps - 1 + 15) & ~15;
+    p.m_tiles = ceil_div(d->T, CS_SUPER_M);
+    p.num_tiles = p.m_tiles * d->batch * d->groups;
+    p.bo_mode = d->reserved;
+    CUtensorMap tx, tw;
+    int rc;
+    if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, p.slab_rows / 2, "x")) != A2V_OK) return rc;
+    if ((rc = cs_make_map(&tw, d->w, d->ldw, (long long)d->groups * d->w_group_rows, 1, d->ldw, 64, "w")) != A2V_OK)
+        return rc;
+    const int smem = 2 * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_EPI_BYTES + 1024;
+    static int configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            a2v_set_error("conv_slab: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+            return A2V_ERR_CUDA;
+        }
+        configured = smem;
+    }
+    const int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
+    conv_slab_fwd_kernel<<<grid, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+    return a2v_check_launch("conv_slab_fwd");
+}

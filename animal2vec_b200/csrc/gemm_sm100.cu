@@ -353,8 +353,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const TileCoord t = decode_tile(p, tile);
             int kb0, kb1;
             tile_k_range(p, t, kb0, kb1);
-            mbar_wait(&tfull_bar[as], aphase);
-            tc_fence_after();
             const int row0_in_block = t.m_tile * BLOCK_M + q * 32;  // first row of this warp's 32-row slab
             int rows_ok = p.M - row0_in_block;
             rows_ok = rows_ok > 32 ? 32 : rows_ok;
@@ -370,7 +368,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const long long row_off0 = row_g * p.ldc;
             const bool has_work = (kb1 > kb0);
             const uint32_t st = smem_u32(epi_stage + (warp - 2) * (32 * EPI_PITCH));
-#pragma unroll 1
+            // residual epilogue: a load issued inside the chunk loop costs a full memory latency per chunk
+            // (measured 4x the GEMM itself); issue every load of the tile NOW, before waiting for the MMAs
+            constexpr bool PREFETCH = (EPI == EPI_RES);
+            uint2 aux[PREFETCH ? BLOCK_N / 32 : 1][8];
+            if (PREFETCH) {
+                const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + row_off0 + col_base;
+#pragma unroll
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    const int lcol = t.n_tile * BLOCK_N + c * 32 + (lane & 7) * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = (lane >> 3) + 4 * i;
+                        aux[PREFETCH ? c : 0][i] = (r < rows_ok && lcol + 4 <= p.N)
+                                                        ? __ldg(reinterpret_cast<const uint2*>(rp + (long long)r * p.ldc + lcol))
+                                                        : make_uint2(0u, 0u);
+                    }
+                }
+            }
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+#pragma unroll(PREFETCH ? BLOCK_N / 32 : 1)
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t raw[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, raw);
@@ -395,7 +413,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int lcol = col0 + (lane & 7) * 4;
                 const int cols_ok = p.N - lcol;
                 if (rows_ok > 0 && has_work) {
-                    if (EPI >= 0) {
+                    if (PREFETCH) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 lo = unpack_bf16x2(aux[PREFETCH ? c : 0][i].x);
+                            const float2 hi = unpack_bf16x2(aux[PREFETCH ? c : 0][i].y);
+                            v[4 * i] = v[4 * i] * p.alpha + lo.x;
+                            v[4 * i + 1] = v[4 * i + 1] * p.alpha + lo.y;
+                            v[4 * i + 2] = v[4 * i + 2] * p.alpha + hi.x;
+                            v[4 * i + 3] = v[4 * i + 3] * p.alpha + hi.y;
+                        }
+                        GemmParams q0 = p;  // alpha already applied; plain store of the sum
+                        q0.alpha = 1.0f;
+                        epilogue_chunk<bf16, 0>(q0, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
+                    } else if (EPI >= 0) {
                         epilogue_chunk<bf16, EPI>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     } else if (p.out_atomic || p.out_accumulate) {
                         epilogue_chunk_f32_accum(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);

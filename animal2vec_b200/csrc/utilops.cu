@@ -106,6 +106,24 @@ __global__ void __launch_bounds__(256) relayout_kernel(const RelayoutParams p) {
 }
 
 // ---------------------------------------------------------------- flat elementwise
+// out = dh * GELU'(u): backward of timm Mlp's activation (modules.py:312-317), applied to the output of
+// the fc2 data-gradient GEMM (kept out of that GEMM's epilogue: a latency-bound read there costs 5x more).
+template <typename T>
+__global__ void __launch_bounds__(256) dgelu_mul_kernel(const T* __restrict__ dh, const T* __restrict__ u,
+                                                        T* __restrict__ out, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        load4(dh + 8 * i, *reinterpret_cast<float(*)[4]>(a));
+        load4(dh + 8 * i + 4, *reinterpret_cast<float(*)[4]>(a + 4));
+        load4(u + 8 * i, *reinterpret_cast<float(*)[4]>(b));
+        load4(u + 8 * i + 4, *reinterpret_cast<float(*)[4]>(b + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= gelu_grad_t<T>(b[j]);
+        store4(out + 8 * i, *reinterpret_cast<float(*)[4]>(a));
+        store4(out + 8 * i + 4, *reinterpret_cast<float(*)[4]>(a + 4));
+    }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                                             long long n4) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -322,6 +340,19 @@ extern "C" int a2v_relayout(int in_dtype, int out_dtype, const void* in, void* o
         return A2V_ERR_ARG;
     }
     return a2v_check_launch("relayout");
+}
+
+extern "C" int a2v_dgelu_mul(int dtype, const void* dh, const void* u, void* out, int64_t n, a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "dgelu_mul: bad dtype");
+    A2V_REQUIRE(dh && u && out && n >= 0 && n % 8 == 0, "dgelu_mul: n must be a multiple of 8");
+    if (n == 0) return A2V_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int grid = flat_grid(n / 8);
+    if (dtype == A2V_F32)
+        dgelu_mul_kernel<float><<<grid, 256, 0, st>>>((const float*)dh, (const float*)u, (float*)out, n / 8);
+    else
+        dgelu_mul_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dh, (const bf16*)u, (bf16*)out, n / 8);
+    return a2v_check_launch("dgelu_mul");
 }
 
 extern "C" int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream) {

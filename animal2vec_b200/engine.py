@@ -338,6 +338,8 @@ class PretrainEngine:
         w = (W.dgrad if dgrad else W.fwd)[name]
         if self.fp32:
             x = self._split_a(x, (W.split_d if dgrad else W.split)[name])
+        elif gemm.conv_slab_ok(x, w, taps, groups):
+            return gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias)
         return gemm.conv_nt(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias)
 
     def wgrad(self, dy, x, out):
@@ -611,7 +613,7 @@ class PretrainEngine:
                                 dbeta=G(pre + "norm2.bias"))
         ops.colsum(dt, G(pre + "mlp.fc2.bias"))
         self.wgrad(dt, s.h, G(pre + "mlp.fc2.weight"))
-        du = self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True, dgelu_u=s.u)
+        du = ops.dgelu_mul(self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True), s.u)
         ops.colsum(du, G(pre + "mlp.fc1.bias"))
         self.wgrad(du, s.x1, G(pre + "mlp.fc1.weight"))
         dx1 = self.lin(du, W, pre + "mlp.fc1.weight", dgrad=True, residual=dz2)

@@ -39,6 +39,12 @@ def _launch(d: L.GemmDesc, anchor: torch.Tensor) -> None:
     L.require_device(anchor)
     L.launch_count += 1
     tl = L.gemm_timeline
+    if L.op_timeline is not None:
+        tag = (f"a2v_gemm[mode={d.mode},M={d.M},N={d.N},K={d.k_per_tap if d.mode == 0 else d.red_rows},taps={d.taps},"
+               f"G={d.groups},B={d.batch},epi={int(bool(d.bias))}{int(d.act)}{int(bool(d.preact))}{int(bool(d.dgelu_u))}"
+               f"{int(bool(d.residual))},tapM={d.a_tap_cols}]")
+        L.timed_call(tag, lambda: L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm"))
+        return
     if tl is None:
         L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm")
         return
@@ -164,6 +170,50 @@ def conv_nt(
     d.alpha = 1.0
     d.bias = bias.data_ptr() if bias is not None else None
     _launch(d, x)
+    return out
+
+
+def conv_slab_ok(x: torch.Tensor, w: torch.Tensor, taps: int, groups: int) -> bool:
+    """The slab kernel covers bf16 tap convs with 64-channel groups and <= 64 outputs per group."""
+    if x.dtype != torch.bfloat16 or x.dim() != 3 or taps > 32:
+        return False
+    cin, nout = x.shape[-1], w.shape[0]
+    return cin == groups * 64 and nout // groups <= 64 and w.shape[1] == taps * 64
+
+
+def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: int,
+              out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+              bias: Optional[torch.Tensor] = None, _bo_mode: int = 0) -> torch.Tensor:
+    """Same operator as :func:`conv_nt` (64-channel groups), every activation row read once per tile."""
+    bsz, t, cin = x.shape
+    assert x.is_contiguous() and w.is_contiguous() and w.dtype == torch.bfloat16
+    nout = w.shape[0]
+    ng = nout // groups
+    if out is None:
+        out = torch.empty(bsz, t, nout, device=x.device, dtype=out_dtype or torch.bfloat16)
+    assert out.is_contiguous() and out.shape == (bsz, t, nout)
+    d = L.ConvDesc()
+    d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.batch, d.T, d.groups, d.taps, d.pad = bsz, t, groups, taps, pad
+    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, 64, ng, ng
+    d.ldx, d.ldw, d.ldy = cin, w.shape[1], nout
+    d.y_dtype = L.dtype_code(out)
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.reserved = _bo_mode
+    L.require_device(x)
+    L.launch_count += 1
+    tl = L.gemm_timeline
+    if L.op_timeline is not None:
+        L.timed_call(f"a2v_conv_slab_fwd[B={bsz},T={t},G={groups},taps={taps},ng={ng}]",
+                     lambda: L.check(L.load().a2v_conv_slab_fwd(C.byref(d), L.stream_ptr()), "a2v_conv_slab_fwd"))
+        return out
+    if tl is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(L.load().a2v_conv_slab_fwd(C.byref(d), L.stream_ptr()), "a2v_conv_slab_fwd")
+    if tl is not None:
+        e1.record()
+        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps))
     return out
 
 

@@ -89,6 +89,29 @@ class GemmDesc(C.Structure):
     ]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p),
+        ("w", C.c_void_p),
+        ("y", C.c_void_p),
+        ("batch", C.c_int),
+        ("T", C.c_int),
+        ("groups", C.c_int),
+        ("taps", C.c_int),
+        ("pad", C.c_int),
+        ("ng", C.c_int),
+        ("x_group_cols", C.c_int),
+        ("w_group_rows", C.c_int),
+        ("y_group_cols", C.c_int),
+        ("ldx", C.c_int64),
+        ("ldw", C.c_int64),
+        ("ldy", C.c_int64),
+        ("y_dtype", C.c_int),
+        ("bias", C.c_void_p),
+        ("reserved", C.c_int),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -96,6 +119,21 @@ _lock = threading.Lock()
 launch_count = 0
 # Optional per-GEMM timing (bench.py roofline leg): list of (start_event, end_event, flops) when enabled.
 gemm_timeline = None
+# Optional per-call timing of EVERY C-ABI call (tools/profile_step.py): list of (name, start, end) events.
+op_timeline = None
+
+
+def timed_call(name, fn):
+    """Run ``fn`` (one C-ABI launch) bracketed by CUDA events when op_timeline is enabled."""
+    tl = op_timeline
+    if tl is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    tl.append((name, e0, e1))
+    return r
 
 
 def exported_symbols() -> list[str]:

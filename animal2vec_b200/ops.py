@@ -77,6 +77,16 @@ def _call(name: str, anchor: torch.Tensor, *args) -> None:
     L.require_device(anchor)
     fn = getattr(L.load(), name)
     L.launch_count += 1
+    if L.op_timeline is not None:
+        tag = name
+        if name.startswith("a2v_rowln"):
+            d = args[0]._obj
+            tag = f"{name}[C={d.channels},act={d.act},aff={int(bool(d.gamma))},b={int(bool(d.b))},rows={d.rows}]"
+        elif name.startswith("a2v_attn"):
+            d = args[0]._obj
+            tag = f"{name}[L={d.L},batch={d.batch}]"
+        L.timed_call(tag, lambda: L.check(fn(*args, L.stream_ptr()), name))
+        return
     L.check(fn(*args, L.stream_ptr()), name)
 
 
@@ -262,6 +272,14 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     c = x.shape[-1]
     assert x.is_contiguous() and out.dtype == torch.float32 and out.numel() == c
     _call("a2v_colsum", x, L.dtype_code(x), _p(x), _p(out), C.c_int64(x.numel() // c), c)
+    return out
+
+
+def dgelu_mul(dh: torch.Tensor, u: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = dh * GELU'(u) (in place on ``dh`` when ``out`` is None)."""
+    assert dh.is_contiguous() and u.is_contiguous() and dh.shape == u.shape and dh.dtype == u.dtype
+    out = dh if out is None else out
+    _call("a2v_dgelu_mul", dh, L.dtype_code(dh), _p(dh), _p(u), _p(out), C.c_int64(dh.numel()))
     return out
 
 

@@ -102,6 +102,31 @@ typedef struct {
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Grouped stride-1 tap convolution with 64-channel groups, activation rows loaded once per tile
+ * ("slab" implicit GEMM, tcgen05/TMA): forward and data gradient of the positional-encoder convs
+ * (nn/modalities/audio.py:93-113) and of Decoder1d's convs (nn/modalities/modules.py:141-157).
+ *   y[b, t, g*y_group_cols + n] = sum_{j<taps, c<64} x[b, t+j-pad, g*64+c] * w[g*w_group_rows+n, j*64+c] (+bias)
+ * x: (batch, T, ldx) bf16, w: (groups*w_group_rows, ldw) bf16 tap-major rows, y: (batch, T, ldy) bf16/fp32.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    const void* x;
+    const void* w;
+    void* y;
+    int batch, T, groups, taps, pad;
+    int ng;               /* outputs per group, <= 64 */
+    int x_group_cols;     /* must be 64 */
+    int w_group_rows;
+    int y_group_cols;
+    int64_t ldx, ldw, ldy;
+    int y_dtype;
+    const float* bias;    /* per global y column, or NULL */
+    int reserved;         /* 0 */
+} a2v_conv_desc;
+
+int a2v_conv_slab_supported(const a2v_conv_desc* d);
+int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Fused row LayerNorm family (HBM-bound, warp-per-row):
  *   z = a + dropout_b(b);  n = LN(z) * gamma + beta;  y = dropout_out(act(n)) + post
  * Replaces: Fp32LayerNorm+PSwish / +GELU of the feature extractor (nn/utils.py:1105-1117,
@@ -209,6 +234,8 @@ int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t*
  *  a2v_sumsq / a2v_clip_coef: gradient-norm clipping without a host round trip.
  * ------------------------------------------------------------------------------------ */
 int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream);
+/* out = dh * GELU'(u) elementwise (backward of timm Mlp's GELU, nn/modalities/modules.py:312-317). */
+int a2v_dgelu_mul(int dtype, const void* dh, const void* u, void* out, int64_t n, a2v_stream_t stream);
 int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
                      const int64_t* in_strides4, int64_t in_offset, a2v_stream_t stream);
 /* general 4-D re-layout with cast: out[out_offset + i.out_strides] (+)= in[in_offset + i.in_strides]

@@ -104,3 +104,22 @@ def test_conv_wgrad_tn(bsz, t, cg, ng, groups, taps):
     out = torch.zeros(groups * taps * cg, ng, device="cuda")
     gemm.conv_wgrad_tn(dy, x, out, taps=taps, pad=pad, groups=groups)
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
+
+
+@pytest.mark.parametrize("bsz,t,ng,groups,taps,pad", [(2, 300, 64, 4, 19, 9), (3, 130, 64, 2, 7, 3), (1, 2000, 64, 16, 19, 9),
+                                                       (2, 257, 48, 3, 7, 3), (2, 512, 64, 1, 3, 1), (1, 700, 64, 2, 19, 9)])
+def test_conv_slab(bsz, t, ng, groups, taps, pad):
+    """Slab implicit GEMM (rows loaded once, tap = shifted shared-memory descriptor) against torch conv1d."""
+    from animal2vec_b200 import gemm
+
+    cg = 64
+    x = _randn(bsz, t, groups * cg, seed=11)
+    wt = _randn(groups * ng, cg, taps, scale=0.05, seed=12)
+    bias = torch.randn(groups * ng, device="cuda")
+    ref = F.conv1d(x.float().transpose(1, 2), wt.float(), bias, padding=pad, groups=groups).transpose(1, 2)
+    w = wt.permute(0, 2, 1).reshape(groups * ng, taps * cg).contiguous()
+    assert gemm.conv_slab_ok(x, w, taps, groups)
+    out = gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=torch.float32, bias=bias)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+    out16 = gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, bias=bias)
+    assert _rel(out16, ref) < 5e-3

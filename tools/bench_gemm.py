@@ -33,6 +33,20 @@ def main():
         res.append({"op": "nt", "m": m, "n": n, "k": k, "bn": bn, "ms": ms, "tflops": 2 * m * n * k / ms / 1e9,
                     "torch_ms": ms_t, "torch_tflops": 2 * m * n * k / ms_t / 1e9})
         print(res[-1], flush=True)
+    # epilogue variants at the fc1 shape
+    m, n, k = 28416, 4096, 1024
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") * 0.03).bfloat16()
+    bias = torch.randn(n, device="cuda")
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty_like(out)
+    for name, kw in [("plain", {}), ("bias", dict(bias=bias)), ("bias+gelu", dict(bias=bias, act=1)),
+                     ("bias+gelu+preact", dict(bias=bias, act=1, preact=pre)), ("dgelu", dict(dgelu_u=pre)),
+                     ("residual", dict(residual=pre))]:
+        ms = bench(lambda: gemm.gemm_nt(a, w, out=out, **kw))
+        res.append({"op": "nt-epi " + name, "m": m, "n": n, "k": k, "ms": ms, "tflops": 2 * m * n * k / ms / 1e9})
+        print(res[-1], flush=True)
+    del a, w, out, pre
     for (r, m, n, bn) in [(54528, 1024, 1024, 256), (54528, 4096, 1024, 256), (54528, 1024, 4096, 256)]:
         a = torch.randn(r, m, device="cuda").bfloat16()
         b = torch.randn(r, n, device="cuda").bfloat16()
@@ -48,6 +62,15 @@ def main():
     fl = 2 * 24 * 2000 * 1024 * 64 * 19
     res.append({"op": "conv_nt", "ms": ms, "tflops": fl / ms / 1e9})
     print(res[-1], flush=True)
+    for mode in (0,):
+        try:
+            o2 = gemm.conv_slab(x, w, taps=19, pad=9, groups=16, _bo_mode=mode)
+            err = ((o2.float() - out.float()).norm() / out.float().norm()).item()
+            ms = bench(lambda: gemm.conv_slab(x, w, taps=19, pad=9, groups=16, out=o2, _bo_mode=mode))
+            res.append({"op": f"conv_slab(bo_mode={mode})", "ms": ms, "tflops": fl / ms / 1e9, "rel_vs_conv_nt": err})
+            print(res[-1], flush=True)
+        except Exception as ex:
+            print("conv_slab failed", mode, ex, flush=True)
     dw = torch.zeros(16 * 19 * 64, 64, device="cuda")
     ms = bench(lambda: gemm.conv_wgrad_tn(x, x, dw, taps=19, pad=9, groups=16))
     res.append({"op": "conv_wgrad_tn", "ms": ms, "tflops": fl / ms / 1e9})
