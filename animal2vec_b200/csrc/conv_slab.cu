@@ -255,6 +255,171 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient of the same operator, x as the MMA M side with the taps folded into M:
+//   dW_T[(g*taps + j)*64 + c, n] += sum_{b,t} x[b, t + j - pad, g*64 + c] * dy[b, t, g*DG + n]
+// One CTA owns (group, block of 16 taps, K split). Per 64-row k-block it loads ONE x slab (64 + 15 halo
+// rows) and one dy tile; M tile i pairs tap i with tap i+8 (the second 64-wide M chunk is the same slab
+// 8 rows = 1024 B further down, so the descriptor's leading-dimension byte offset is 1024 and the swizzle
+// phase is unchanged). Up to 8 accumulators (512 TMEM columns) stay resident over the whole K range; the
+// epilogue adds them to the fp32 gradient with atomics (split-K).
+// ---------------------------------------------------------------------------------------------
+constexpr int CW_STAGES = 8;
+constexpr int CW_SLAB_ROWS = 80;                       // 64 + 15 halo, rounded to 8
+constexpr int CW_SLAB_BYTES = CW_SLAB_ROWS * 128;      // 10 KB
+constexpr int CW_DY_BYTES = 64 * 128;                  // 8 KB
+constexpr int CW_STAGE_BYTES = CW_SLAB_BYTES + CW_DY_BYTES;
+
+struct ConvWgradParams {
+    int batch, T, groups, taps, pad, ng;
+    int dy_group_cols;
+    float* out;          // (groups*taps*64, ldo) fp32
+    long long ldo;
+    int kb_per_batch;    // ceil(T / 64)
+    int n_tb;            // tap blocks (<= 2)
+    int nt[2];           // M tiles per tap block
+    int splits[2];       // K splits per tap block
+    int num_tiles;
+};
+
+__global__ void __launch_bounds__(CS_THREADS, 1)
+conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy,
+                       const ConvWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CW_STAGES * CW_STAGE_BYTES);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + CW_STAGES;
+    uint64_t* tfull = empty_bar + CW_STAGES;  // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmDy);
+        for (int i = 0; i < CW_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // one tile per CTA (grid == num_tiles): tile -> (tap block, group, split)
+    int tile = blockIdx.x;
+    int tb = 0;
+    if (tile >= p.groups * p.splits[0]) {
+        tile -= p.groups * p.splits[0];
+        tb = 1;
+    }
+    const int g = tile % p.groups;
+    const int split = tile / p.groups;
+    const int nt = p.nt[tb];
+    const int total_kb = p.batch * p.kb_per_batch;
+    const int per = (total_kb + p.splits[tb] - 1) / p.splits[tb];
+    const int kb0 = split * per;
+    const int kb1 = min(total_kb, kb0 + per);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int b = kb / p.kb_per_batch;
+                const int r0 = (kb - b * p.kb_per_batch) * 64;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sx = smem + stage * CW_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], CW_STAGE_BYTES);
+                tma_load_3d(sx, &tmX, &full_bar[stage], g * 64, r0 + tb * 16 - p.pad, b);
+                tma_load_3d(sx + CW_SLAB_BYTES, &tmDy, &full_bar[stage], g * p.dy_group_cols, r0, b);
+                if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 64, true, true);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sx = smem_u32(smem + stage * CW_STAGE_BYTES);
+                const uint32_t sd = sx + CW_SLAB_BYTES;
+                for (int i = 0; i < nt; ++i) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // A: M-major, 16 K rows per step (2048 B), M chunk 1 = 8 rows (1024 B) below chunk 0
+                        const uint64_t da = umma_smem_desc(sx + (uint32_t)i * 128u + k * 2048, 1024, 1024);
+                        const uint64_t db = umma_smem_desc(sd + k * 2048, 0, 1024);
+                        umma_bf16(tmem_base + i * 64, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+        __syncwarp();
+    } else if (kb1 > kb0) {
+        const int q = warp & 3;
+        const uint32_t st = smem_u32(epi_stage + (warp - 2) * (32 * CS_EPI_PITCH));
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int i = 0; i < nt; ++i) {
+            const int tap = tb * 16 + i + (q >= 2 ? 8 : 0);
+            const int ch0 = (q & 1) * 32;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + i * 64 + c * 32, raw);
+                tmem_ld_wait();
+                if (tap >= p.taps || c * 32 >= p.ng) continue;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (lane * CS_EPI_PITCH + 4 * j) * 4),
+                                 "r"(raw[4 * j]), "r"(raw[4 * j + 1]), "r"(raw[4 * j + 2]), "r"(raw[4 * j + 3])
+                                 : "memory");
+                __syncwarp();
+                float v[32];
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(v[4 * r]), "=f"(v[4 * r + 1]), "=f"(v[4 * r + 2]), "=f"(v[4 * r + 3])
+                                 : "r"(st + (((lane >> 3) + 4 * r) * CS_EPI_PITCH + (lane & 7) * 4) * 4)
+                                 : "memory");
+                __syncwarp();
+                const int lcol = c * 32 + (lane & 7) * 4;
+                float* orow = p.out + ((long long)(g * p.taps + tap) * 64 + ch0) * p.ldo + lcol;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    float* o = orow + (long long)((lane >> 3) + 4 * r) * p.ldo;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (lcol + j < p.ng) atomicAdd(o + j, v[4 * r + j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -337,4 +502,61 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     const int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
     conv_slab_fwd_kernel<<<grid, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
     return a2v_check_launch("conv_slab_fwd");
+}
+
+extern "C" int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t ldo, a2v_stream_t stream) {
+    // d->x: activations (batch, T, ldx); d->w: dy (batch, T, ldw) bf16 with w_group_rows = columns of dy per
+    // group; out: (groups*taps*64, ldo) fp32, atomically accumulated
+    A2V_REQUIRE(d != nullptr && d->x && d->w && out, "conv_slab_wgrad: NULL pointer");
+    A2V_REQUIRE(a2v_conv_slab_supported(d), "conv_slab_wgrad: needs 64-channel groups, ng <= 64, taps <= 32");
+    A2V_REQUIRE(d->ldw % 8 == 0 && ldo >= d->ng, "conv_slab_wgrad: bad strides");
+    ConvWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.batch = d->batch; p.T = d->T; p.groups = d->groups; p.taps = d->taps; p.pad = d->pad; p.ng = d->ng;
+    p.dy_group_cols = d->w_group_rows;
+    p.out = out; p.ldo = ldo;
+    p.kb_per_batch = ceil_div(d->T, 64);
+    p.n_tb = ceil_div(d->taps, 16);
+    for (int tb = 0; tb < 2; ++tb) {
+        const int rem = d->taps - 16 * tb;
+        p.nt[tb] = tb < p.n_tb ? (rem < 8 ? rem : 8) : 0;
+        p.splits[tb] = 0;
+    }
+    // K splits per tap block: fill the SMs once, minimise the longest CTA (work ~ M tiles / splits)
+    const int sms = a2v_num_sms();
+    const int total_kb = p.batch * p.kb_per_batch;
+    int max_s = sms / d->groups;
+    if (max_s < p.n_tb) max_s = p.n_tb;
+    if (p.n_tb == 1) {
+        p.splits[0] = max_s < total_kb ? max_s : total_kb;
+    } else {
+        double best = 1e30;
+        for (int s0 = 1; s0 < max_s; ++s0) {
+            const int s1 = max_s - s0;
+            const double w0 = (double)p.nt[0] / s0, w1 = (double)p.nt[1] / s1;
+            const double w = w0 > w1 ? w0 : w1;
+            if (w < best) { best = w; p.splits[0] = s0; p.splits[1] = s1; }
+        }
+        if (p.splits[0] > total_kb) p.splits[0] = total_kb;
+        if (p.splits[1] > total_kb) p.splits[1] = total_kb;
+    }
+    if (p.splits[0] < 1) p.splits[0] = 1;
+    if (p.n_tb > 1 && p.splits[1] < 1) p.splits[1] = 1;
+    p.num_tiles = d->groups * (p.splits[0] + p.splits[1]);
+    CUtensorMap tx, tdy;
+    int rc;
+    if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, CW_SLAB_ROWS, "x")) != A2V_OK) return rc;
+    if ((rc = cs_make_map(&tdy, d->w, d->ldw, d->T, d->batch, d->ldw, 64, "dy")) != A2V_OK) return rc;
+    const int smem = CW_STAGES * CW_STAGE_BYTES + 256 + CS_EPI_BYTES + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_slab_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            a2v_set_error("conv_slab_wgrad: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+            return A2V_ERR_CUDA;
+        }
+        configured = true;
+    }
+    conv_slab_wgrad_kernel<<<p.num_tiles, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tdy, p);
+    return a2v_check_launch("conv_slab_wgrad");
 }

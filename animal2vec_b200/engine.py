@@ -354,6 +354,9 @@ class PretrainEngine:
             b, t, n = dy.shape
             dy = ops.split3(dy.reshape(-1, n), 2).view(3 * b, t, n)
             x = ops.split3(x.reshape(-1, x.shape[-1]), 3).view(3 * b, t, x.shape[-1])
+        elif x.shape[-1] == groups * 64 and dy.shape[-1] // groups <= 64 and taps <= 32:
+            gemm.conv_slab_wgrad(dy, x, out, taps=taps, pad=pad, groups=groups)
+            return
         gemm.conv_wgrad_tn(dy, x, out, taps=taps, pad=pad, groups=groups)
 
     def _seed(self, site: int) -> int:

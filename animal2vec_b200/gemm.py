@@ -217,6 +217,38 @@ def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: 
     return out
 
 
+def conv_slab_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, taps: int, pad: int, groups: int) -> torch.Tensor:
+    """Same contract as :func:`conv_wgrad_tn` (transposed (G*taps*64, Ng) fp32 output) for 64-channel groups:
+    one x slab per 64-row k-block serves all taps of a 16-tap block."""
+    bsz, t, cin = x.shape
+    nout = dy.shape[-1]
+    ng = nout // groups
+    assert cin == groups * 64 and ng <= 64 and dy.shape[:2] == x.shape[:2] and dy.is_contiguous() and x.is_contiguous()
+    assert out.dtype == torch.float32 and out.shape == (groups * taps * 64, ng) and out.is_contiguous()
+    d = L.ConvDesc()
+    d.x, d.w, d.y = x.data_ptr(), dy.data_ptr(), None
+    d.batch, d.T, d.groups, d.taps, d.pad = bsz, t, groups, taps, pad
+    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, 64, ng, ng
+    d.ldx, d.ldw, d.ldy = cin, nout, ng
+    d.y_dtype = L.F32
+    L.require_device(x)
+    L.launch_count += 1
+    fn = lambda: L.check(L.load().a2v_conv_slab_wgrad(C.byref(d), C.c_void_p(out.data_ptr()), C.c_int64(ng),
+                                                      L.stream_ptr()), "a2v_conv_slab_wgrad")
+    tl = L.gemm_timeline
+    if L.op_timeline is not None:
+        L.timed_call(f"a2v_conv_slab_wgrad[B={bsz},T={t},G={groups},taps={taps},ng={ng}]", fn)
+    elif tl is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps))
+    else:
+        fn()
+    return out
+
+
 def _pick_splits(tiles: int, kblocks: int) -> int:
     sms = 148
     if tiles >= sms:

@@ -125,6 +125,10 @@ typedef struct {
 
 int a2v_conv_slab_supported(const a2v_conv_desc* d);
 int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream);
+/* weight gradient of the same operator: d->x = activations, d->w = dy (batch, T, ldw) with w_group_rows =
+ * dy columns per group; out[(g*taps + j)*64 + c, n] += sum_{b,t} x[b, t+j-pad, g*64+c] * dy[b, t, g*w_group_rows+n]
+ * (fp32, (groups*taps*64, ldo), atomically accumulated: split-K over (batch, time)). */
+int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t ldo, a2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused row LayerNorm family (HBM-bound, warp-per-row):

@@ -123,3 +123,22 @@ def test_conv_slab(bsz, t, ng, groups, taps, pad):
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
     out16 = gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, bias=bias)
     assert _rel(out16, ref) < 5e-3
+
+
+@pytest.mark.parametrize("bsz,t,ng,groups,taps,pad", [(2, 300, 64, 4, 19, 9), (3, 130, 64, 2, 7, 3), (2, 2000, 64, 16, 19, 9),
+                                                       (2, 257, 48, 3, 7, 3), (5, 64, 64, 1, 3, 1), (1, 700, 64, 2, 25, 12)])
+def test_conv_slab_wgrad(bsz, t, ng, groups, taps, pad):
+    from animal2vec_b200 import gemm
+
+    cg = 64
+    x = _randn(bsz, t, groups * cg, seed=13)
+    dy = _randn(bsz, t, groups * ng, seed=14)
+    wt = torch.zeros(groups * ng, cg, taps, device="cuda", requires_grad=True)
+    y = F.conv1d(x.float().transpose(1, 2), wt, None, padding=pad, groups=groups)
+    y.backward(dy.float().transpose(1, 2))
+    ref = wt.grad.view(groups, ng, cg, taps).permute(0, 3, 2, 1).reshape(groups * taps * cg, ng)
+    out = torch.zeros(groups * taps * cg, ng, device="cuda")
+    gemm.conv_slab_wgrad(dy, x, out, taps=taps, pad=pad, groups=groups)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+    gemm.conv_slab_wgrad(dy, x, out, taps=taps, pad=pad, groups=groups)  # accumulates
+    assert _rel(out, 2 * ref) < 1e-5

@@ -75,6 +75,9 @@ def main():
     ms = bench(lambda: gemm.conv_wgrad_tn(x, x, dw, taps=19, pad=9, groups=16))
     res.append({"op": "conv_wgrad_tn", "ms": ms, "tflops": fl / ms / 1e9})
     print(res[-1], flush=True)
+    ms = bench(lambda: gemm.conv_slab_wgrad(x, x, dw, taps=19, pad=9, groups=16))
+    res.append({"op": "conv_slab_wgrad", "ms": ms, "tflops": fl / ms / 1e9})
+    print(res[-1], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/bench_gemm.json", "w"), indent=1)
 
