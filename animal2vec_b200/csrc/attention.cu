@@ -91,7 +91,7 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // O is rescaled in TMEM only when a row's maximum grows by more than 2^8 (lazy rescaling), the S MMA of
 // the next tile is issued before the softmax of this one finishes, K and V tiles have separate
 // barriers so the next K can land while V is still being consumed.
-template <bool HAS_POS, bool DROP>
+template <bool HAS_POS, bool DROP, bool TRIM>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -163,6 +163,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const long long bh = (long long)b * p.H + h;
 
     float m_run = -INFINITY, l_run = 0.f;
+    // warps whose 32 query rows all lie beyond L (second q tile of a short sequence) only keep the barriers moving
+    const bool warp_active = !TRIM || (q0 + warp * 32) < L;  // TRIM: short sequences (student), skip dead work
 
     for (int j = 0; j < n_kv; ++j) {
         const int buf = j & 1;
@@ -187,6 +189,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         const int nvalid = L - k0;  // keys of this tile that exist (>= 128 except for the last tile)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
+            if (TRIM && (!warp_active || c * 32 >= nvalid)) {  // nothing real in this 32-key chunk
+#pragma unroll
+                for (int i = 0; i < 32; ++i) t[c * 32 + i] = -INFINITY;
+                continue;
+            }
             uint32_t raw[32];
             tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
             tmem_ld_wait();
@@ -213,7 +220,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         }
         // lazy rescaling of O (in TMEM) and of the running sum
         const bool grow = m_tile > m_run + ATT_RESCALE_THRESHOLD;  // also true on the first tile (m_run = -inf)
-        if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        if (j > 0 && warp_active && __any_sync(0xffffffffu, grow)) {
             const float alpha = grow ? ex2_approx(m_run - m_tile) : 1.0f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -234,6 +241,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint8_t* prow = smem + ATT_SMEM_P + (c >> 1) * 16384 + tid * 128;
+            if (TRIM && !warp_active) continue;  // rows beyond L: their P rows only feed O rows that are never stored
+            if (TRIM && c * 32 >= nvalid) {      // keys beyond L: exact zeros (they sit inside the K extent of P.V)
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(prow + (((c & 1) * 4 + u) ^ (tid & 7)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 float e[8];
@@ -476,6 +490,345 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_wmma_kernel(const AttnParams 
 }
 
 // ------------------------------------------------------------------------------------------
+// backward, tcgen05 (student shapes: L <= 160 kept tokens), persistent over (batch, head)
+//
+// Per head all five products run on tcgen05 with TMEM accumulators; Q, K, V, dO are TMA-loaded ONCE
+// as [row][64] 128B-swizzled tiles and serve as K-major or MN-major operands as each product needs:
+//   S  = Q K^T          (A = Q K-major,  B = K K-major,  N = 160)   -> P = exp(S*scale + alibi - lse)
+//   dP = dO V^T         (A = dO K-major, B = V K-major)              -> dS = P * (dP*keep - delta)
+//   dV += Pd^T dO       (A = Pd MN-major, B = dO MN-major)     Pd = P with the dropout mask applied
+//   dK += dS^T Q        (A = dS MN-major, B = Q MN-major)
+//   dQ  = dS K          (A = dS K-major,  B = K MN-major)
+// P/Pd/dS live in shared memory as bf16 in the layout the forward kernel uses for P (one thread per
+// query row writes its row). Query rows are processed in two tiles (rows 0..127, 128..159); rows and
+// keys >= L are zero so they contribute nothing to the K-dimension sums.
+// ------------------------------------------------------------------------------------------
+constexpr int BT_THREADS = 288;                 // warps 0-7: two threads per query row (column halves); warp 8: TMA + MMA issue
+constexpr int BT_ROWT = 256;
+constexpr int BT_NK = 160;                      // padded key count (UMMA N of S / dP)
+constexpr int BT_OP_BYTES = 16384 + 4096;       // one operand: rows 0..127 then rows 128..159
+constexpr int BT_SM_Q = 0;
+constexpr int BT_SM_K = BT_OP_BYTES;
+constexpr int BT_SM_V = 2 * BT_OP_BYTES;
+constexpr int BT_SM_DO = 3 * BT_OP_BYTES;
+constexpr int BT_SM_P = 4 * BT_OP_BYTES;        // 3 chunks of 64 keys x 128 rows x 128 B  (81920: 1024-aligned)
+constexpr int BT_SM_DS = BT_SM_P + 3 * 16384;
+constexpr int BT_SM_END = BT_SM_DS + 3 * 16384 + 16384;  // +16 KB: M-side over-read of key tile 1 stays in bounds
+constexpr int BT_SM_BAR = BT_SM_END;
+constexpr int BT_SMEM_TOTAL = BT_SM_BAR + 256 + 1024;
+constexpr int BT_TM_S = 0, BT_TM_DQ = 192, BT_TM_DK = 256, BT_TM_DV = 384;
+
+template <bool DROP>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmQ32,
+                        const __grid_constant__ CUtensorMap tmG128, const __grid_constant__ CUtensorMap tmG32,
+                        const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BT_SM_BAR);
+    uint64_t* bar_load = bars;      // TMA -> everyone
+    uint64_t* bar_s = bars + 1;     // S ready
+    uint64_t* bar_p = bars + 2;     // P written (128 arrivals)
+    uint64_t* bar_dp = bars + 3;    // dP ready
+    uint64_t* bar_ds = bars + 4;    // dS written (128 arrivals)
+    uint64_t* bar_dq = bars + 5;    // dQ of this tile ready (and every MMA issued so far retired)
+    uint64_t* bar_epi = bars + 6;   // row threads done with TMEM / operands of this head (128 arrivals)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    __shared__ int s_pos[BT_NK];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = p.L, D = p.D;
+    const int n_mt = L > 128 ? 2 : 1;
+    const int n_kt = n_mt;
+    const int heads_total = p.batch * p.H;
+
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, BT_ROWT);
+        mbar_init(bar_dp, 1);
+        mbar_init(bar_ds, BT_ROWT);
+        mbar_init(bar_dq, 1);
+        mbar_init(bar_epi, BT_ROWT);
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sbase = smem_u32(smem);
+
+    if (warp == 8) {
+        // ================================================================ control warp
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ128);
+            tma_prefetch_desc(&tmQ32);
+            tma_prefetch_desc(&tmG128);
+            tma_prefetch_desc(&tmG32);
+            const uint32_t id_s = umma_idesc_bf16(128, BT_NK, false, false);
+            const uint32_t id_dq = umma_idesc_bf16(128, 64, false, true);
+            const uint32_t id_t = umma_idesc_bf16(128, 64, true, true);
+            uint32_t it = 0;   // heads processed by this CTA
+            uint32_t ph_tile = 0;  // parity for the per-tile barriers (bar_p, bar_ds)
+            for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+                const int b = head / p.H, h = head - b * p.H;
+                if (it > 0) mbar_wait(bar_epi, (it - 1) & 1);  // previous head fully drained
+                tc_fence_after();
+                const uint32_t bytes = (uint32_t)(4 * 16384 + (n_mt > 1 ? 4 * 4096 : 0));
+                mbar_expect_tx(bar_load, bytes);
+                tma_load_3d(smem + BT_SM_Q, &tmQ128, bar_load, h * HD, 0, b);
+                tma_load_3d(smem + BT_SM_K, &tmQ128, bar_load, D + h * HD, 0, b);
+                tma_load_3d(smem + BT_SM_V, &tmQ128, bar_load, 2 * D + h * HD, 0, b);
+                tma_load_3d(smem + BT_SM_DO, &tmG128, bar_load, h * HD, 0, b);
+                if (n_mt > 1) {
+                    tma_load_3d(smem + BT_SM_Q + 16384, &tmQ32, bar_load, h * HD, 128, b);
+                    tma_load_3d(smem + BT_SM_K + 16384, &tmQ32, bar_load, D + h * HD, 128, b);
+                    tma_load_3d(smem + BT_SM_V + 16384, &tmQ32, bar_load, 2 * D + h * HD, 128, b);
+                    tma_load_3d(smem + BT_SM_DO + 16384, &tmG32, bar_load, h * HD, 128, b);
+                }
+                mbar_wait(bar_load, it & 1);
+                tc_fence_after();
+                for (int m = 0; m < n_mt; ++m) {
+                    const uint32_t qa = sbase + BT_SM_Q + m * 16384, ga = sbase + BT_SM_DO + m * 16384;
+                    const int krows = m == 0 ? 8 : 2;  // 16-row K steps over the query rows of this tile
+                    // S_m = Q_m K^T
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + BT_TM_S, umma_smem_desc(qa + k * 32, 0, 1024),
+                                  umma_smem_desc(sbase + BT_SM_K + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+                    umma_commit(bar_s);
+                    // P written -> dP_m = dO_m V^T (same TMEM columns), dV += Pd_m^T dO_m
+                    mbar_wait(bar_p, ph_tile);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + BT_TM_S, umma_smem_desc(ga + k * 32, 0, 1024),
+                                  umma_smem_desc(sbase + BT_SM_V + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+                    umma_commit(bar_dp);
+                    for (int kt = 0; kt < n_kt; ++kt)
+                        for (int k = 0; k < krows; ++k)
+                            umma_bf16(tmem_base + BT_TM_DV + kt * 64,
+                                      umma_smem_desc(sbase + BT_SM_P + kt * 32768 + k * 2048, 16384, 1024),
+                                      umma_smem_desc(ga + k * 2048, 0, 1024), id_t, (m > 0 || k > 0) ? 1u : 0u);
+                    // dS written -> dQ_m = dS_m K, dK += dS_m^T Q_m
+                    mbar_wait(bar_ds, ph_tile);
+                    tc_fence_after();
+                    // K extent = keys actually loaded (zero-filled up to the next multiple of 16): never multiply
+                    // a zero dS column with stale shared memory
+                    for (int ks = 0; ks < ((L + 15) >> 4); ++ks)
+                        umma_bf16(tmem_base + BT_TM_DQ,
+                                  umma_smem_desc(sbase + BT_SM_DS + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
+                                  umma_smem_desc(sbase + BT_SM_K + ks * 2048, 0, 1024), id_dq, ks > 0 ? 1u : 0u);
+                    for (int kt = 0; kt < n_kt; ++kt)
+                        for (int k = 0; k < krows; ++k)
+                            umma_bf16(tmem_base + BT_TM_DK + kt * 64,
+                                      umma_smem_desc(sbase + BT_SM_DS + kt * 32768 + k * 2048, 16384, 1024),
+                                      umma_smem_desc(qa + k * 2048, 0, 1024), id_t, (m > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(bar_dq);  // retires after everything issued so far
+                    ph_tile ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ row threads
+        const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+        const int rt = tid & 127;        // row inside the 128-row tile
+        const int half = tid >> 7;       // 0: key chunks 0..2 (dK rows), 1: key chunks 3..4 (dV rows)
+        const int c_lo = half ? 3 : 0, c_hi = half ? BT_NK / 32 : 3;
+        const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+        const bf16* dout = reinterpret_cast<const bf16*>(p.dout);
+        const bf16* outp = reinterpret_cast<const bf16*>(p.out);
+        bf16* dqkv = reinterpret_cast<bf16*>(p.dqkv);
+        uint32_t it = 0, ph_s = 0, ph_dp = 0, ph_dq = 0;
+        for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+            const int b = head / p.H, h = head - b * p.H;
+            const long long bh = head;
+            const float coef = head_coef(p, h);
+            float dc_part = 0.f;
+            for (int j = tid; j < BT_NK; j += BT_ROWT)
+                s_pos[j] = j < L ? (p.pos != nullptr ? p.pos[(long long)b * L + j] : j) : 0;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int m = 0; m < n_mt; ++m) {
+                const int i = m * 128 + rt;           // query row
+                const bool row_ok = i < L;
+                const bool row_used = m == 0 || rt < 32;   // rows inside the K extent of this tile
+                float delta = 0.f, lse_i = 0.f;
+                int pos_i = 0;
+                if (row_ok) {
+                    const bf16* go = dout + ((long long)b * L + i) * D + h * HD;
+                    const bf16* oo = outp + ((long long)b * L + i) * D + h * HD;
+#pragma unroll
+                    for (int d = 0; d < HD; d += 8) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(go + d);
+                        const uint4 c = *reinterpret_cast<const uint4*>(oo + d);
+                        const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
+                                     a3 = unpack_bf16x2(a.w);
+                        const float2 c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y), c2 = unpack_bf16x2(c.z),
+                                     c3 = unpack_bf16x2(c.w);
+                        delta += a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y + a2.x * c2.x + a2.y * c2.y +
+                                 a3.x * c3.x + a3.y * c3.y;
+                    }
+                    lse_i = p.lse[bh * L + i] * LOG2E;
+                    pos_i = s_pos[i];
+                }
+                const float scale2 = p.sm_scale * LOG2E, coef2 = coef * LOG2E;
+                uint8_t* prow = smem + BT_SM_P + rt * 128;
+                uint8_t* drow = smem + BT_SM_DS + rt * 128;
+                uint32_t keepbits[2] = {0xffffffffu, 0xffffffffu};  // dropout keep flags of this thread's <= 3 chunks... (see below)
+                uint32_t keepbits2 = 0xffffffffu;
+
+                // ---- P (undropped, parked in the dS buffer) and Pd (dropout applied) from S
+                mbar_wait(bar_s, ph_s);
+                ph_s ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_S + c * 32, raw);
+                    tmem_ld_wait();
+                    if (!row_used) continue;
+                    uint32_t kb = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float pv[8], pd[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int j = c * 32 + u * 8 + e;
+                            float pr = 0.f;
+                            if (row_ok && j < L) {
+                                const int pj = s_pos[j];
+                                const float t = fmaf(__uint_as_float(raw[u * 8 + e]), scale2,
+                                                     -coef2 * fabsf((float)(pos_i - pj)));
+                                pr = ex2_approx(t - lse_i);
+                            }
+                            pv[e] = pr;
+                            bool keep = true;
+                            if (DROP) {
+                                keep = attn_keep(p.seed, bh, L, i, j, p.drop_p);
+                                kb |= (keep ? 1u : 0u) << (u * 8 + e);
+                            }
+                            pd[e] = keep ? pr * inv_keep : 0.f;
+                        }
+                        uint4 v, w;
+                        v.x = pack_bf16x2(pd[0], pd[1]); v.y = pack_bf16x2(pd[2], pd[3]);
+                        v.z = pack_bf16x2(pd[4], pd[5]); v.w = pack_bf16x2(pd[6], pd[7]);
+                        w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
+                        w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
+                        const int unit = ((c & 1) * 4 + u) ^ (rt & 7);
+                        *reinterpret_cast<uint4*>(prow + (c >> 1) * 16384 + unit * 16) = v;
+                        *reinterpret_cast<uint4*>(drow + (c >> 1) * 16384 + unit * 16) = w;
+                    }
+                    if (c - c_lo == 0) keepbits[0] = kb;
+                    else if (c - c_lo == 1) keepbits[1] = kb;
+                    else keepbits2 = kb;
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_p);
+
+                // ---- dS = P * (dP * keep - delta), d(alibi scale)
+                mbar_wait(bar_dp, ph_dp);
+                ph_dp ^= 1;
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_S + c * 32, raw);
+                    tmem_ld_wait();
+                    if (!row_used) continue;
+                    const uint32_t kb = (c - c_lo == 0) ? keepbits[0] : ((c - c_lo == 1) ? keepbits[1] : keepbits2);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int unit = ((c & 1) * 4 + u) ^ (rt & 7);
+                        uint4* slot = reinterpret_cast<uint4*>(drow + (c >> 1) * 16384 + unit * 16);
+                        const uint4 pw = *slot;
+                        const float2 p0 = unpack_bf16x2(pw.x), p1 = unpack_bf16x2(pw.y), p2 = unpack_bf16x2(pw.z),
+                                     p3 = unpack_bf16x2(pw.w);
+                        const float pr[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+                        float ds[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int j = c * 32 + u * 8 + e;
+                            float dp = __uint_as_float(raw[u * 8 + e]);
+                            if (DROP) dp = ((kb >> (u * 8 + e)) & 1u) ? dp * inv_keep : 0.f;
+                            ds[e] = (row_ok && j < L) ? pr[e] * (dp - delta) : 0.f;
+                            if (row_ok && j < L) dc_part -= ds[e] * fabsf((float)(pos_i - s_pos[j]));
+                        }
+                        uint4 v;
+                        v.x = pack_bf16x2(ds[0], ds[1]); v.y = pack_bf16x2(ds[2], ds[3]);
+                        v.z = pack_bf16x2(ds[4], ds[5]); v.w = pack_bf16x2(ds[6], ds[7]);
+                        *slot = v;
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_ds);
+
+                // ---- dQ rows of this tile (also: every MMA that reads P / dS has retired)
+                mbar_wait(bar_dq, ph_dq);
+                ph_dq ^= 1;
+                tc_fence_after();
+                {
+                    const int c = half;
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_DQ + c * 32, raw);
+                    tmem_ld_wait();
+                    if (row_ok) {
+                        bf16* o = dqkv + ((long long)b * L + i) * 3 * D + h * HD + c * 32;
+#pragma unroll
+                        for (int d = 0; d < 32; d += 4) {
+                            float v[4] = {__uint_as_float(raw[d]) * p.sm_scale, __uint_as_float(raw[d + 1]) * p.sm_scale,
+                                          __uint_as_float(raw[d + 2]) * p.sm_scale, __uint_as_float(raw[d + 3]) * p.sm_scale};
+                            store4(o + d, v);
+                        }
+                    }
+                }
+                tc_fence_before();
+            }
+            // ---- dK, dV rows (key tile kt, row tid)
+            for (int kt = 0; kt < n_kt; ++kt) {
+                const int j = kt * 128 + rt;
+                {
+                    const int which = half;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t raw[32];
+                        tmem_ld_32x32(tmem_base + lane_off + (which == 0 ? BT_TM_DK : BT_TM_DV) + kt * 64 + c * 32, raw);
+                        tmem_ld_wait();
+                        if (j < L) {
+                            const float sc = which == 0 ? p.sm_scale : 1.0f;
+                            bf16* o = dqkv + ((long long)b * L + j) * 3 * D + (which + 1) * D + h * HD + c * 32;
+#pragma unroll
+                            for (int d = 0; d < 32; d += 4) {
+                                float v[4] = {__uint_as_float(raw[d]) * sc, __uint_as_float(raw[d + 1]) * sc,
+                                              __uint_as_float(raw[d + 2]) * sc, __uint_as_float(raw[d + 3]) * sc};
+                                store4(o + d, v);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+            // d(alibi_scale[h]) += slope_h * sum(-dS * dist)  (only where the clamped scale is active)
+            dc_part = warp_sum(dc_part);
+            if (lane == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr &&
+                p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
+                atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, dc_part * p.slopes[h]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // fp32 validation-mode kernels (CUDA cores, one thread per query row)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn_fwd_ref_kernel(const AttnParams p) {
@@ -647,8 +1000,11 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         cudaError_t e = cudaSuccess;
 #define A2V_ATT_CFG(P_, D_)                                                                                   \
     if (e == cudaSuccess)                                                                                     \
-        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 ATT_SMEM_TOTAL);
+        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_, false>,                                      \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL);                \
+    if (e == cudaSuccess)                                                                                     \
+        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_, true>,                                       \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL);
         A2V_ATT_CFG(false, false) A2V_ATT_CFG(false, true) A2V_ATT_CFG(true, false) A2V_ATT_CFG(true, true)
 #undef A2V_ATT_CFG
         if (e != cudaSuccess) {
@@ -658,10 +1014,17 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         configured = true;
     }
     const bool has_pos = p.pos != nullptr, drop = p.drop_p > 0.f;
-    if (has_pos && drop) attn_fwd_tcgen05_kernel<true, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
-    else if (has_pos) attn_fwd_tcgen05_kernel<true, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
-    else if (drop) attn_fwd_tcgen05_kernel<false, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
-    else attn_fwd_tcgen05_kernel<false, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);
+    const bool trim = p.L <= 512;
+#define A2V_ATT_GO(P_, D_)                                                                       \
+    do {                                                                                         \
+        if (trim) attn_fwd_tcgen05_kernel<P_, D_, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);  \
+        else attn_fwd_tcgen05_kernel<P_, D_, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);      \
+    } while (0)
+    if (has_pos && drop) A2V_ATT_GO(true, true);
+    else if (has_pos) A2V_ATT_GO(true, false);
+    else if (drop) A2V_ATT_GO(false, true);
+    else A2V_ATT_GO(false, false);
+#undef A2V_ATT_GO
     return a2v_check_launch("attn_fwd_tcgen05");
 }
 
@@ -677,22 +1040,55 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         return a2v_check_launch("attn_bwd_ref");
     }
     A2V_REQUIRE(p.L <= BWD_LMAX,
-                "attention backward (bf16): the shared-memory-resident kernel supports at most %d tokens per "
+                "attention backward (bf16): the shared-memory-resident kernels support at most %d tokens per "
                 "sequence, got %d", BWD_LMAX, p.L);
-    const int LP = (p.L + 15) & ~15;
-    const size_t smem = (size_t)4 * LP * BWD_LD * 2 + (size_t)2 * LP * (LP + 8) * 2 + 8 * 2 * 16 * BWD_SCR * 4 +
-                        (size_t)3 * LP * 4 + 128;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_wmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) {
-            a2v_set_error("attention backward: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
+    static EncodeTiledFn2 encode = nullptr;
+    if (encode == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym) {
+            a2v_set_error("attention: cuTensorMapEncodeTiled not available");
             return A2V_ERR_CUDA;
         }
-        configured = smem;
+        encode = reinterpret_cast<EncodeTiledFn2>(sym);
     }
-    dim3 grid(p.H, p.batch);
-    attn_bwd_wmma_kernel<<<grid, 256, smem, st>>>(p);
-    return a2v_check_launch("attn_bwd_wmma");
+    A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dout) & 15) == 0,
+                "attention backward: qkv / dout not 16-byte aligned");
+    CUtensorMap maps[4];
+    for (int i = 0; i < 4; ++i) {
+        const bool is_q = i < 2;
+        const int cols = is_q ? 3 * p.D : p.D;
+        cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)p.L, (cuuint64_t)p.batch};
+        cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)p.L * cols * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)((i & 1) ? 32 : 128), 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                            const_cast<void*>(is_q ? p.qkv : p.dout), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            a2v_set_error("attention backward: cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return A2V_ERR_CUDA;
+        }
+    }
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             BT_SMEM_TOTAL);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     BT_SMEM_TOTAL);
+        if (e != cudaSuccess) {
+            a2v_set_error("attention backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+            return A2V_ERR_CUDA;
+        }
+        configured = true;
+    }
+    const int heads = p.batch * p.H;
+    const int grid = heads < a2v_num_sms() ? heads : a2v_num_sms();
+    if (p.drop_p > 0.f)
+        attn_bwd_tcgen05_kernel<true><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    else
+        attn_bwd_tcgen05_kernel<false><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+    return a2v_check_launch("attn_bwd_tcgen05");
 }
