@@ -62,9 +62,11 @@ constexpr int ATT_SMEM_Q = 0;
 constexpr int ATT_SMEM_K = 16384;             // 2 buffers
 constexpr int ATT_SMEM_V = 16384 * 3;         // 2 buffers
 constexpr int ATT_SMEM_P = 16384 * 5;         // 2 chunks of 64 keys
-constexpr int ATT_SMEM_POS = 16384 * 7;       // 2 x 128 ints
-constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 1024;
-constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128 + 1024;
+constexpr int ATT_SMEM_POS = 16384 * 7;       // 128 floats (key positions of the current tile)
+constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 512;
+// 112.6 KB: two CTAs per SM need 2 x (dynamic + 1 KB reserved) <= 228 KB, i.e. <= 113 KB each. The dynamic
+// window of a kernel without static shared memory starts 1024-aligned (checked at run time, trap otherwise).
+constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximum may lag by up to 2^8
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -94,8 +96,9 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 template <bool HAS_POS, bool DROP, bool TRIM>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128B-swizzled tiles need 1024-byte alignment
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
     uint64_t* bar_q = bars;
     uint64_t* bar_k = bars + 1;  // [2]
@@ -103,7 +106,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     uint64_t* bar_s = bars + 5;
     uint64_t* bar_o = bars + 6;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-    int* spos = reinterpret_cast<int*>(smem + ATT_SMEM_POS);
+    float* spos = reinterpret_cast<float*>(smem + ATT_SMEM_POS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -172,7 +175,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         const bool last = (j == n_kv - 1);
         if (HAS_POS) {
             const int kj = k0 + tid;
-            spos[buf * 128 + tid] = kj < L ? p.pos[(long long)b * L + kj] : -(1 << 28);
+            // single buffer: the __syncthreads before the P.V issue of the previous tile orders its readers
+            spos[tid] = kj < L ? (float)p.pos[(long long)b * L + kj] : -268435456.0f;
             __syncthreads();
         }
         mbar_wait(bar_s, j & 1);
@@ -186,6 +190,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         float t[128];
         float m_tile = -INFINITY;
         const float dist0 = (float)(pos_i - k0);
+        const float fpos_i = (float)pos_i;
         const int nvalid = L - k0;  // keys of this tile that exist (>= 128 except for the last tile)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -201,7 +206,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             for (int i = 0; i < 32; ++i) {
                 const int col = c * 32 + i;
                 float dist;
-                if (HAS_POS) dist = (float)(pos_i - spos[buf * 128 + col]);
+                if (HAS_POS) dist = fpos_i - spos[col];
                 else dist = dist0 - (float)col;
                 float v = fmaf(__uint_as_float(raw[i]), scale2, -coef2 * fabsf(dist));
                 if (last && col >= nvalid) v = -INFINITY;
