@@ -162,6 +162,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const int pos_i = q_ok ? (HAS_POS ? p.pos[(long long)b * L + qi] : qi) : 0;
     const float coef2 = head_coef(p, h) * LOG2E;
     const float scale2 = p.sm_scale * LOG2E;
+    const float kappa = coef2 / scale2;
     const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const long long bh = (long long)b * p.H + h;
 
@@ -186,32 +187,58 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
         }
 
-        // scores -> registers (log2 units, ALiBi added), row maximum
+        // scores -> registers, row maximum. t[] holds u with  score(log2 units) = u * e_mul + c_row:
+        //  * generic tiles (token positions, the diagonal tile, the ragged last tile): u = score, e_mul = 1, c_row = 0;
+        //  * every other tile of a contiguous sequence lies entirely before or after this CTA's query rows, so
+        //    |i - j| is linear in the key column: score = scale2 * (raw + sg*kappa*col) + c_row with a per-row
+        //    constant c_row -- two FFMAs and half an FMNMX per element, the constant folds into the exp2 offset.
         float t[128];
         float m_tile = -INFINITY;
+        float e_mul = 1.0f, c_row = 0.f;
         const float dist0 = (float)(pos_i - k0);
         const float fpos_i = (float)pos_i;
         const int nvalid = L - k0;  // keys of this tile that exist (>= 128 except for the last tile)
+        if (!HAS_POS && !last && j != (int)blockIdx.x) {
+            const float sg = j < (int)blockIdx.x ? 1.0f : -1.0f;
+            const float kap = sg * kappa;
+            float m_u = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            if (TRIM && (!warp_active || c * 32 >= nvalid)) {  // nothing real in this 32-key chunk
+            for (int c = 0; c < 4; ++c) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) t[c * 32 + i] = -INFINITY;
-                continue;
+                for (int i = 0; i < 32; ++i) {
+                    const float u = fmaf(kap, (float)(c * 32 + i), __uint_as_float(raw[i]));
+                    t[c * 32 + i] = u;
+                    m_u = fmaxf(m_u, u);
+                }
             }
-            uint32_t raw[32];
-            tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
-            tmem_ld_wait();
+            e_mul = scale2;
+            c_row = -sg * coef2 * dist0;
+            m_tile = fmaf(m_u, scale2, c_row);
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int col = c * 32 + i;
-                float dist;
-                if (HAS_POS) dist = fpos_i - spos[col];
-                else dist = dist0 - (float)col;
-                float v = fmaf(__uint_as_float(raw[i]), scale2, -coef2 * fabsf(dist));
-                if (last && col >= nvalid) v = -INFINITY;
-                t[col] = v;
-                m_tile = fmaxf(m_tile, v);
+            for (int c = 0; c < 4; ++c) {
+                if (TRIM && (!warp_active || c * 32 >= nvalid)) {  // nothing real in this 32-key chunk
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) t[c * 32 + i] = -INFINITY;
+                    continue;
+                }
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_s + lane_off + c * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = c * 32 + i;
+                    float dist;
+                    if (HAS_POS) dist = fpos_i - spos[col];
+                    else dist = dist0 - (float)col;
+                    float v = fmaf(__uint_as_float(raw[i]), scale2, -coef2 * fabsf(dist));
+                    if (last && col >= nvalid) v = -INFINITY;
+                    t[col] = v;
+                    m_tile = fmaxf(m_tile, v);
+                }
             }
         }
         // previous P.V done: P smem, V[buf^1] and the O accumulator are ours again
@@ -243,6 +270,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
 
         // probabilities -> shared memory (bf16, 128B-swizzled K-major A operand of P.V)
         float l_tile = 0.f;
+        const float e_off = c_row - m_run;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             uint8_t* prow = smem + ATT_SMEM_P + (c >> 1) * 16384 + tid * 128;
@@ -258,7 +286,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 float e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = ex2_approx(t[c * 32 + u * 8 + i] - m_run);
+                    e[i] = ex2_approx(fmaf(t[c * 32 + u * 8 + i], e_mul, e_off));
                     l_tile += e[i];
                 }
                 if (DROP) {
