@@ -432,6 +432,281 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p, con
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Specialised bf16 kernels for the two row shapes that dominate the step: LayerNorm(no affine) + GELU
+// over the student's positional-conv rows (1024 contiguous channels) and over the group-padded decoder
+// rows (16 groups x 48 real of 64 stored channels, optional residual). Compared with the generic kernels
+// above everything is resolved at compile time (no run-time feature tests inside the unrolled loops, a
+// fifth of the SASS, under 128 registers so two CTAs share an SM), every lane owns 16-byte chunks of
+// REAL channels only (pad chunks cost no arithmetic) and GELU costs 14
+// instructions (erfc form: y = relu(x) - |x| * erfc(|x|/sqrt2)/2).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// h(x) = erfc(|x|/sqrt2)/2 (Abramowitz-Stegun 7.1.26, halved coefficients) and e = exp(-x^2/2)
+__device__ __forceinline__ float half_erfc(float x, float& e) {
+    const float a = fabsf(x);
+    const float t = rcp_approx(fmaf(0.23164188f, a, 1.0f));
+    e = ex2_approx_f((x * -0.72134752f) * x);
+    float pl = fmaf(0.5307027145f, t, -0.7265760135f);
+    pl = fmaf(pl, t, 0.7107068705f);
+    pl = fmaf(pl, t, -0.142248368f);
+    pl = fmaf(pl, t, 0.127414796f);
+    return (pl * t) * e;
+}
+__device__ __forceinline__ float gelu_erfc(float x) {
+    float e;
+    const float h = half_erfc(x, e);
+    return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float gelu_erfc_grad(float x) {
+    float e;
+    const float h = half_erfc(x, e);
+    const float cdf = x >= 0.f ? 1.0f - h : h;
+    return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+
+struct ChunkMap {
+    int cs, cr, ngroups;  // stored / real 16-byte chunks per channel group, groups per row
+    __device__ __forceinline__ int stored_chunk(int r) const { return (r / cr) * cs + (r % cr); }
+};
+
+// ring slot fill: ONE bulk copy per tensor row (pads included -- one copy per channel group of the real bytes
+// only was measured 45% slower: the copy issue rate, not the bytes, limits a 2 KB row)
+template <int NTENS>
+__device__ __forceinline__ void fast_issue(unsigned char* slot, uint64_t* bar, const unsigned char* const* src,
+                                           long long row, long long rows, int row_bytes, int lane) {
+    if (lane == 0 && row < rows) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)(NTENS * row_bytes));
+#pragma unroll
+        for (int t = 0; t < NTENS; ++t)
+            bulk_load_1d(slot + (size_t)t * row_bytes, src[t] + row * row_bytes, (uint32_t)row_bytes, bar);
+    }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    return v;
+}
+
+constexpr int FAST_STAGES_MAX = 8;
+
+// forward: y = GELU(LN(a)) (+ post); NV = 16-byte real chunks per lane (32 * NV * 8 real channels per row)
+template <int NV, bool HAS_POST>
+__global__ void __launch_bounds__(256, 2) rowln_gelu_fwd_kernel(const RowLnParams p, const int stages, const ChunkMap cm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NTENS = HAS_POST ? 2 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
+    const int row_bytes = p.C * 2;
+    unsigned char* ring = smem_raw + (size_t)warp * stages * NTENS * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ROWLN_WARPS * stages * NTENS * row_bytes) + warp * FAST_STAGES_MAX;
+    const unsigned char* src[NTENS];
+    src[0] = reinterpret_cast<const unsigned char*>(p.a);
+    if (HAS_POST) src[NTENS - 1] = reinterpret_cast<const unsigned char*>(p.post);
+    int off[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) off[i] = cm.stored_chunk(lane + 32 * i) * 16;
+    const int npad = (cm.cs - cm.cr) * cm.ngroups;
+    const float inv_c = 1.0f / (float)(NV * 256);
+    unsigned char* Y = reinterpret_cast<unsigned char*>(p.y);
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    for (int s = 0; s < stages; ++s)
+        fast_issue<NTENS>(ring + (size_t)s * NTENS * row_bytes, &bars[s], src, warp0 + (long long)s * nwarps, p.rows, row_bytes, lane);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        mbar_wait(&bars[slot], (uint32_t)((it / stages) & 1));
+        const unsigned char* sm = ring + (size_t)slot * NTENS * row_bytes;
+        uint4 va[NV], vp[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            va[i] = *reinterpret_cast<const uint4*>(sm + off[i]);
+            if (HAS_POST) vp[i] = *reinterpret_cast<const uint4*>(sm + row_bytes + off[i]);
+        }
+        __syncwarp();
+        fast_issue<NTENS>(ring + (size_t)slot * NTENS * row_bytes, &bars[slot], src, row + (long long)stages * nwarps, p.rows,
+                          row_bytes, lane);
+        float z[NV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            unpack8(va[i], z[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += z[i][j];
+        }
+        const float mean = warp_sum(s) * inv_c;
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                z[i][j] -= mean;
+                v = fmaf(z[i][j], z[i][j], v);
+            }
+        const float rstd = rsqrtf(warp_sum(v) * inv_c + p.eps);
+        if (lane == 0) {
+            if (p.mean != nullptr) p.mean[row] = mean;
+            if (p.rstd != nullptr) p.rstd[row] = rstd;
+        }
+        unsigned char* yrow = Y + row * row_bytes;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float o[8], po[8];
+            if (HAS_POST) unpack8(vp[i], po);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                o[j] = gelu_erfc(z[i][j] * rstd);
+                if (HAS_POST) o[j] += po[j];
+            }
+            *reinterpret_cast<uint4*>(yrow + off[i]) = pack8(o);
+        }
+        for (int q = lane; q < npad; q += 32) {  // pad chunks stay exact zeros
+            const int g = q / (cm.cs - cm.cr), k = q % (cm.cs - cm.cr);
+            *reinterpret_cast<uint4*>(yrow + (size_t)(g * cm.cs + cm.cr + k) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// backward: da = dLN(dy * GELU'(n)) from the saved row statistics
+template <int NV>
+__global__ void __launch_bounds__(256, 2) rowln_gelu_bwd_kernel(const RowLnParams p, const int stages, const ChunkMap cm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NTENS = 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
+    const int row_bytes = p.C * 2;
+    unsigned char* ring = smem_raw + (size_t)warp * stages * NTENS * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ROWLN_WARPS * stages * NTENS * row_bytes) + warp * FAST_STAGES_MAX;
+    const unsigned char* src[2] = {reinterpret_cast<const unsigned char*>(p.a), reinterpret_cast<const unsigned char*>(p.dy)};
+    int off[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) off[i] = cm.stored_chunk(lane + 32 * i) * 16;
+    const int npad = (cm.cs - cm.cr) * cm.ngroups;
+    const float inv_c = 1.0f / (float)(NV * 256);
+    unsigned char* DA = reinterpret_cast<unsigned char*>(p.da);
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    for (int s = 0; s < stages; ++s)
+        fast_issue<NTENS>(ring + (size_t)s * NTENS * row_bytes, &bars[s], src, warp0 + (long long)s * nwarps, p.rows, row_bytes, lane);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        const float mean = p.mean[row], rstd = p.rstd[row];
+        mbar_wait(&bars[slot], (uint32_t)((it / stages) & 1));
+        const unsigned char* sm = ring + (size_t)slot * NTENS * row_bytes;
+        uint4 va[NV], vg[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            va[i] = *reinterpret_cast<const uint4*>(sm + off[i]);
+            vg[i] = *reinterpret_cast<const uint4*>(sm + row_bytes + off[i]);
+        }
+        __syncwarp();
+        fast_issue<NTENS>(ring + (size_t)slot * NTENS * row_bytes, &bars[slot], src, row + (long long)stages * nwarps, p.rows,
+                          row_bytes, lane);
+        float xh[NV][8], g[NV][8];
+        float s1 = 0.f, s2 = 0.f;
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            unpack8(va[i], xh[i]);
+            unpack8(vg[i], g[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[i][j] = fmaf(xh[i][j], rstd, nmr);
+                g[i][j] *= gelu_erfc_grad(xh[i][j]);
+                s1 += g[i][j];
+                s2 = fmaf(g[i][j], xh[i][j], s2);
+            }
+        }
+        s1 = warp_sum(s1) * inv_c;
+        s2 = warp_sum(s2) * inv_c;
+        unsigned char* drow = DA + row * row_bytes;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+            *reinterpret_cast<uint4*>(drow + off[i]) = pack8(o);
+        }
+        for (int q = lane; q < npad; q += 32) {
+            const int gq = q / (cm.cs - cm.cr), k = q % (cm.cs - cm.cr);
+            *reinterpret_cast<uint4*>(drow + (size_t)(gq * cm.cs + cm.cr + k) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
+// dispatch test + launch of the specialised kernels; returns -1 when the generic path must be used
+static int launch_rowln_fast(const RowLnParams& p, bool bwd, cudaStream_t st) {
+    if (p.act != 1 || p.gamma != nullptr || p.beta != nullptr || p.b != nullptr) return -1;
+    if (p.drop_out > 0.f) return -1;
+    if (bwd && (p.da == nullptr || p.db != nullptr)) return -1;
+    if (p.gw % 8 || p.gr % 8 || p.C % p.gw) return -1;
+    ChunkMap cm;
+    cm.cs = p.gw / 8; cm.cr = p.gr / 8; cm.ngroups = p.C / p.gw;
+    const int real_chunks = cm.cr * cm.ngroups;
+    if (real_chunks % 32 || real_chunks / 32 < 1 || real_chunks / 32 > 4) return -1;
+    const int nv = real_chunks / 32;
+    const int ntens = bwd ? 2 : (p.post != nullptr ? 2 : 1);
+    const int row_bytes = p.C * 2;
+    const size_t per_stage = (size_t)ROWLN_WARPS * ntens * row_bytes;
+    int stages = (int)((110 * 1024 - ROWLN_WARPS * FAST_STAGES_MAX * 8) / per_stage);
+    if (stages > FAST_STAGES_MAX) stages = FAST_STAGES_MAX;
+    if (stages < 2) return -1;
+    const size_t smem = per_stage * stages + (size_t)ROWLN_WARPS * FAST_STAGES_MAX * 8;
+    long long blocks_needed = ceil_div64(p.rows, ROWLN_WARPS);
+    long long cap = (long long)a2v_num_sms() * 2;
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+#define A2V_FAST(KERNEL)                                                                                         \
+    do {                                                                                                         \
+        auto k = KERNEL;                                                                                         \
+        static size_t conf = 0;                                                                                  \
+        if (smem > conf) {                                                                                       \
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+                a2v_set_error("rowln(fast): cudaFuncSetAttribute(%zu) failed", smem);                            \
+                return A2V_ERR_CUDA;                                                                             \
+            }                                                                                                    \
+            conf = smem;                                                                                         \
+        }                                                                                                        \
+        k<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages, cm);                                                   \
+    } while (0)
+#define A2V_FAST_NV(N)                                                          \
+    do {                                                                        \
+        if (bwd) A2V_FAST((rowln_gelu_bwd_kernel<N>));                          \
+        else if (p.post != nullptr) A2V_FAST((rowln_gelu_fwd_kernel<N, true>)); \
+        else A2V_FAST((rowln_gelu_fwd_kernel<N, false>));                       \
+    } while (0)
+    switch (nv) {
+        case 1: A2V_FAST_NV(1); break;
+        case 2: A2V_FAST_NV(2); break;
+        case 3: A2V_FAST_NV(3); break;
+        default: A2V_FAST_NV(4); break;
+    }
+#undef A2V_FAST
+#undef A2V_FAST_NV
+    return a2v_check_launch(bwd ? "rowln_bwd(fast)" : "rowln_fwd(fast)");
+}
+
 template <typename T>
 static int launch_rowln(const RowLnParams& p, bool bwd, cudaStream_t st) {
     const int nch = ceil_div(p.C, 128);
@@ -541,6 +816,10 @@ extern "C" int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     if (d->rows == 0) return A2V_OK;
     RowLnParams p = to_params(d);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d->dtype == A2V_BF16) {
+        rc = launch_rowln_fast(p, false, st);
+        if (rc >= 0) return rc;
+    }
     return d->dtype == A2V_F32 ? launch_rowln<float>(p, false, st) : launch_rowln<bf16>(p, false, st);
 }
 
@@ -553,5 +832,9 @@ extern "C" int a2v_rowln_bwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     if (d->rows == 0) return A2V_OK;
     RowLnParams p = to_params(d);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (d->dtype == A2V_BF16) {
+        rc = launch_rowln_fast(p, true, st);
+        if (rc >= 0) return rc;
+    }
     return d->dtype == A2V_F32 ? launch_rowln<float>(p, true, st) : launch_rowln<bf16>(p, true, st);
 }
