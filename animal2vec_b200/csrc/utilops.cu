@@ -42,6 +42,48 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
     }
 }
 
+// bf16, C % 256 == 0 (every bias-gradient site of the step): 16-byte loads, four independent rows in flight
+// per warp so the ~64 KB per SM that HBM latency needs are outstanding
+__global__ void __launch_bounds__(256) colsum_bf16_wide_kernel(const bf16* __restrict__ x, float* __restrict__ out,
+                                                               long long rows, int C, long long rows_per_block) {
+    __shared__ float part[8][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 256 + lane * 8;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const bf16* base = x + c;
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + 8 * u) * C));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float2 a = unpack_bf16x2(v[u].x), b = unpack_bf16x2(v[u].y), d = unpack_bf16x2(v[u].z),
+                         e = unpack_bf16x2(v[u].w);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+            acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
+        }
+    }
+    for (; r < r1; r += 8) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + r * C));
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), d = unpack_bf16x2(v.z), e = unpack_bf16x2(v.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += d.x; acc[5] += d.y; acc[6] += e.x; acc[7] += e.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) part[warp][lane * 8 + j] = acc[j];
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += part[w][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 256 + threadIdx.x, s);
+}
+
 // ---------------------------------------------------------------- strided cast / permute (4-D)
 struct PermuteParams {
     const void* in;
@@ -262,13 +304,22 @@ extern "C" int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, in
     A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "colsum: bad dtype");
     A2V_REQUIRE(x && out && C > 0 && C % 4 == 0 && rows >= 0, "colsum: bad arguments");
     if (rows == 0) return A2V_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == A2V_BF16 && C % 256 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int cb = C / 256;
+        int rb = (int)((long long)a2v_num_sms() * 4 / cb);
+        if (rb < 1) rb = 1;
+        if (rb > rows / 32 + 1) rb = (int)(rows / 32 + 1);
+        const long long rpb = ceil_div64(rows, rb);
+        colsum_bf16_wide_kernel<<<dim3(cb, rb), 256, 0, st>>>((const bf16*)x, out, rows, C, rpb);
+        return a2v_check_launch("colsum");
+    }
     const int cblocks = ceil_div(C, 128);
     int rblocks = (int)((long long)a2v_num_sms() * 4 / cblocks);
     if (rblocks < 1) rblocks = 1;
     if (rblocks > rows / 8 + 1) rblocks = (int)(rows / 8 + 1);
     const long long rpb = ceil_div64(rows, rblocks);
     dim3 grid(cblocks, rblocks);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == A2V_F32)
         colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, out, rows, C, rpb);
     else

@@ -262,6 +262,11 @@ def test_util_kernels():
     assert _rel(out, 1 + x.sum(0)) < 1e-5
     ops.colsum(x.bfloat16(), out.zero_())
     assert _rel(out, x.bfloat16().float().sum(0)) < 1e-5
+    for rows in (1, 37, 5003):  # bf16, C % 256 == 0: the 16-byte / four-rows-in-flight kernel
+        xw = torch.randn(rows, 768, device="cuda", generator=_g(3)).bfloat16()
+        ow = torch.ones(768, device="cuda")
+        ops.colsum(xw, ow)
+        assert _rel(ow, 1 + xw.float().sum(0)) < 1e-5
 
     w = torch.randn(6, 5, 7, device="cuda", generator=_g(2))  # (O, I, k)
     w_fwd = ops.cast_strided(w, (6, 7, 5), (35, 1, 7), out_dtype=torch.float32)
