@@ -48,11 +48,30 @@ __device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
     return p.slopes != nullptr ? p.slopes[h] * sc : 0.f;
 }
 
+// Attention-dropout bits: 16 bits per (query row, key), generated four keys at a time from 32-bit
+// multiply-xorshift hashes of a per-row key (one hash pair per group of 4 keys, ~3.5 instructions per
+// probability). Every kernel of this file (forward, both backwards, fp32 validation) derives its keep
+// flags from these two functions, so forward and backward always agree.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t attn_row_key(unsigned long long seed, long long bh, int L, int i) {
+    return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + (uint32_t)(bh * L + i)));
+}
+// .x: keys 4g, 4g+1 (low / high half), .y: keys 4g+2, 4g+3
+__device__ __forceinline__ uint2 attn_bits4(uint32_t row_key, int g) {
+    uint32_t a = row_key + (uint32_t)g * 0x9E3779B9U;
+    uint32_t b = a + 0x85ebca6bU;
+    a *= 0x7feb352dU; a ^= a >> 15; a *= 0x846ca68bU; a ^= a >> 16;
+    b *= 0x7feb352dU; b ^= b >> 15; b *= 0x846ca68bU; b ^= b >> 16;
+    return make_uint2(a, b);
+}
+__device__ __forceinline__ uint32_t attn_drop_threshold(float pd) { return (uint32_t)(pd * 65536.0f); }
 __device__ __forceinline__ bool attn_keep(unsigned long long seed, long long bh, int L, int i, int j, float pd) {
-    const unsigned long long stride4 = (unsigned long long)((L + 3) >> 2);
-    const uint64_t hsh = rng64(seed, ((unsigned long long)bh * L + i) * stride4 + (j >> 2));
-    const uint32_t thr = (uint32_t)(pd * 65536.0f);
-    return ((uint32_t)(hsh >> (16 * (j & 3))) & 0xffffu) >= thr;
+    const uint2 bits = attn_bits4(attn_row_key(seed, bh, L, i), j >> 2);
+    const uint32_t w = (j & 2) ? bits.y : bits.x;
+    return ((w >> (16 * (j & 1))) & 0xffffu) >= attn_drop_threshold(pd);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -165,6 +184,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const float kappa = coef2 / scale2;
     const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const long long bh = (long long)b * p.H + h;
+    const uint32_t row_key = DROP ? attn_row_key(p.seed, bh, L, qi) : 0u;
+    const uint32_t drop_thr = attn_drop_threshold(p.drop_p);
 
     float m_run = -INFINITY, l_run = 0.f;
     // warps whose 32 query rows all lie beyond L (second q tile of a short sequence) only keep the barriers moving
@@ -291,8 +312,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 }
                 if (DROP) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        e[i] = attn_keep(p.seed, bh, L, qi, k0 + c * 32 + u * 8 + i, p.drop_p) ? e[i] * inv_keep : 0.f;
+                    for (int g = 0; g < 2; ++g) {
+                        const uint2 bits = attn_bits4(row_key, (k0 + c * 32 + u * 8) / 4 + g);
+                        e[4 * g + 0] = (bits.x & 0xffffu) >= drop_thr ? e[4 * g + 0] * inv_keep : 0.f;
+                        e[4 * g + 1] = (bits.x >> 16) >= drop_thr ? e[4 * g + 1] * inv_keep : 0.f;
+                        e[4 * g + 2] = (bits.y & 0xffffu) >= drop_thr ? e[4 * g + 2] * inv_keep : 0.f;
+                        e[4 * g + 3] = (bits.y >> 16) >= drop_thr ? e[4 * g + 3] * inv_keep : 0.f;
+                    }
                 }
                 uint4 v;
                 v.x = pack_bf16x2(e[0], e[1]);
@@ -536,8 +562,9 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_wmma_kernel(const AttnParams 
 // query row writes its row). Query rows are processed in two tiles (rows 0..127, 128..159); rows and
 // keys >= L are zero so they contribute nothing to the K-dimension sums.
 // ------------------------------------------------------------------------------------------
-constexpr int BT_THREADS = 288;                 // warps 0-7: two threads per query row (column halves); warp 8: TMA + MMA issue
-constexpr int BT_ROWT = 256;
+constexpr int BT_THREADS = 544;                 // warps 0-15: four threads per query row (column quarters); warp 16: TMA + MMA issue
+constexpr int BT_ROWT = 512;
+constexpr int BT_CTRL_WARP = BT_ROWT / 32;
 constexpr int BT_NK = 160;                      // padded key count (UMMA N of S / dP)
 constexpr int BT_OP_BYTES = 16384 + 4096;       // one operand: rows 0..127 then rows 128..159
 constexpr int BT_SM_Q = 0;
@@ -547,14 +574,23 @@ constexpr int BT_SM_DO = 3 * BT_OP_BYTES;
 constexpr int BT_SM_P = 4 * BT_OP_BYTES;        // 3 chunks of 64 keys x 128 rows x 128 B  (81920: 1024-aligned)
 constexpr int BT_SM_DS = BT_SM_P + 3 * 16384;
 constexpr int BT_SM_END = BT_SM_DS + 3 * 16384 + 16384;  // +16 KB: M-side over-read of key tile 1 stays in bounds
-constexpr int BT_SM_BAR = BT_SM_END;
+constexpr int BT_SM_O = BT_SM_END;               // forward output tile (delta = rowsum(dO * O) straight from smem)
+constexpr int BT_SM_BAR = BT_SM_O + BT_OP_BYTES;
 constexpr int BT_SMEM_TOTAL = BT_SM_BAR + 256 + 1024;
 constexpr int BT_TM_S = 0, BT_TM_DQ = 192, BT_TM_DK = 256, BT_TM_DV = 384;
+
+#ifdef A2V_ATTN_TRACE
+__device__ long long g_bt_trace[64];
+#define BT_TR(k) do { if (blockIdx.x == 0 && it == 2) g_bt_trace[k] = clock64(); } while (0)
+#else
+#define BT_TR(k) do { } while (0)
+#endif
 
 template <bool DROP>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmQ32,
                         const __grid_constant__ CUtensorMap tmG128, const __grid_constant__ CUtensorMap tmG32,
+                        const __grid_constant__ CUtensorMap tmO128, const __grid_constant__ CUtensorMap tmO32,
                         const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -564,10 +600,12 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
     uint64_t* bar_p = bars + 2;     // P written (128 arrivals)
     uint64_t* bar_dp = bars + 3;    // dP ready
     uint64_t* bar_ds = bars + 4;    // dS written (128 arrivals)
-    uint64_t* bar_dq = bars + 5;    // dQ of this tile ready (and every MMA issued so far retired)
-    uint64_t* bar_epi = bars + 6;   // row threads done with TMEM / operands of this head (128 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-    __shared__ int s_pos[BT_NK];
+    uint64_t* bar_dq = bars + 5;    // dQ of this tile ready
+    uint64_t* bar_epi = bars + 6;   // row threads done with the dK / dV accumulators of this head
+    uint64_t* bar_free = bars + 7;  // every MMA of a row tile retired: P / dS buffers (and, after the last tile, the operands) are free
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    __shared__ __align__(16) float s_pos[BT_NK];
+    __shared__ float s_delta[4][BT_NK];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = p.L, D = p.D;
@@ -583,249 +621,356 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
         mbar_init(bar_ds, BT_ROWT);
         mbar_init(bar_dq, 1);
         mbar_init(bar_epi, BT_ROWT);
+        mbar_init(bar_free, 1);
         mbar_fence_init();
         fence_proxy_async();
     }
-    if (warp == 8) tmem_alloc<512>(tmem_slot);
+    if (warp == BT_CTRL_WARP) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t sbase = smem_u32(smem);
 
-    if (warp == 8) {
+    if (warp == BT_CTRL_WARP) {
         // ================================================================ control warp
+        // Issue order per row tile m (the tensor pipe retires in order):
+        //   S_m | dP_m | dV += Pd_m^T dO_m | S_{m+1} | dQ_m | dK += dS_m^T Q_m
+        // S of the NEXT tile goes ahead of dQ/dK of this one, dQ is committed before the dK products so its
+        // rows are stored while they run, and the operands of the next head are fetched as soon as the last
+        // product of this head has retired -- before the row threads have drained dK / dV.
         if (lane == 0) {
             tma_prefetch_desc(&tmQ128);
             tma_prefetch_desc(&tmQ32);
             tma_prefetch_desc(&tmG128);
             tma_prefetch_desc(&tmG32);
+            tma_prefetch_desc(&tmO128);
+            tma_prefetch_desc(&tmO32);
             const uint32_t id_s = umma_idesc_bf16(128, BT_NK, false, false);
             const uint32_t id_dq = umma_idesc_bf16(128, 64, false, true);
             const uint32_t id_t = umma_idesc_bf16(128, 64, true, true);
-            uint32_t it = 0;   // heads processed by this CTA
-            uint32_t ph_tile = 0;  // parity for the per-tile barriers (bar_p, bar_ds)
-            for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+            // descriptor bases; a byte offset advances the 14-bit (address >> 4) field (smem < 256 KB: no carry)
+            const uint64_t dK_kmaj = umma_smem_desc(sbase + BT_SM_K, 0, 1024);
+            const uint64_t dV_kmaj = umma_smem_desc(sbase + BT_SM_V, 0, 1024);
+            const uint64_t dQ_base = umma_smem_desc(sbase + BT_SM_Q, 0, 1024);
+            const uint64_t dG_base = umma_smem_desc(sbase + BT_SM_DO, 0, 1024);
+            const uint64_t dP_mn = umma_smem_desc(sbase + BT_SM_P, 16384, 1024);
+            const uint64_t dDS_mn = umma_smem_desc(sbase + BT_SM_DS, 16384, 1024);
+            const uint64_t dDS_k = umma_smem_desc(sbase + BT_SM_DS, 0, 1024);
+#define BT_ADV(desc, bytes) ((desc) + (uint64_t)((uint32_t)(bytes) >> 4))
+            const int ksteps = (L + 15) >> 4;  // 16-key steps of dQ = dS K over the keys actually loaded
+            uint32_t it = 0;       // heads processed by this CTA
+            uint32_t ph_tile = 0;  // parity of the per-tile barriers (bar_p, bar_ds, bar_free)
+            auto issue_s = [&](int m) {
+                const uint64_t qd = BT_ADV(dQ_base, m * 16384);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_base + BT_TM_S, BT_ADV(qd, k * 32), BT_ADV(dK_kmaj, k * 32), id_s, k > 0 ? 1u : 0u);
+                umma_commit(bar_s);
+            };
+            auto load_head = [&](int head) {
                 const int b = head / p.H, h = head - b * p.H;
-                if (it > 0) mbar_wait(bar_epi, (it - 1) & 1);  // previous head fully drained
-                tc_fence_after();
-                const uint32_t bytes = (uint32_t)(4 * 16384 + (n_mt > 1 ? 4 * 4096 : 0));
+                const uint32_t bytes = (uint32_t)(5 * 16384 + (n_mt > 1 ? 5 * 4096 : 0));
                 mbar_expect_tx(bar_load, bytes);
                 tma_load_3d(smem + BT_SM_Q, &tmQ128, bar_load, h * HD, 0, b);
                 tma_load_3d(smem + BT_SM_K, &tmQ128, bar_load, D + h * HD, 0, b);
                 tma_load_3d(smem + BT_SM_V, &tmQ128, bar_load, 2 * D + h * HD, 0, b);
                 tma_load_3d(smem + BT_SM_DO, &tmG128, bar_load, h * HD, 0, b);
+                tma_load_3d(smem + BT_SM_O, &tmO128, bar_load, h * HD, 0, b);
                 if (n_mt > 1) {
                     tma_load_3d(smem + BT_SM_Q + 16384, &tmQ32, bar_load, h * HD, 128, b);
                     tma_load_3d(smem + BT_SM_K + 16384, &tmQ32, bar_load, D + h * HD, 128, b);
                     tma_load_3d(smem + BT_SM_V + 16384, &tmQ32, bar_load, 2 * D + h * HD, 128, b);
                     tma_load_3d(smem + BT_SM_DO + 16384, &tmG32, bar_load, h * HD, 128, b);
+                    tma_load_3d(smem + BT_SM_O + 16384, &tmO32, bar_load, h * HD, 128, b);
                 }
+            };
+            if ((int)blockIdx.x < heads_total) load_head(blockIdx.x);
+            for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+                BT_TR(0);
                 mbar_wait(bar_load, it & 1);
                 tc_fence_after();
+                BT_TR(2);
+                issue_s(0);
+                BT_TR(3);
                 for (int m = 0; m < n_mt; ++m) {
-                    const uint32_t qa = sbase + BT_SM_Q + m * 16384, ga = sbase + BT_SM_DO + m * 16384;
+                    const uint64_t qd = BT_ADV(dQ_base, m * 16384), gd = BT_ADV(dG_base, m * 16384);
                     const int krows = m == 0 ? 8 : 2;  // 16-row K steps over the query rows of this tile
-                    // S_m = Q_m K^T
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + BT_TM_S, umma_smem_desc(qa + k * 32, 0, 1024),
-                                  umma_smem_desc(sbase + BT_SM_K + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
-                    umma_commit(bar_s);
-                    // P written -> dP_m = dO_m V^T (same TMEM columns), dV += Pd_m^T dO_m
+                    // P written -> dP_m = dO_m V^T (the TMEM columns of S), dV += Pd_m^T dO_m
                     mbar_wait(bar_p, ph_tile);
                     tc_fence_after();
+                    BT_TR(4 + 5 * m);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + BT_TM_S, umma_smem_desc(ga + k * 32, 0, 1024),
-                                  umma_smem_desc(sbase + BT_SM_V + k * 32, 0, 1024), id_s, k > 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + BT_TM_S, BT_ADV(gd, k * 32), BT_ADV(dV_kmaj, k * 32), id_s, k > 0 ? 1u : 0u);
                     umma_commit(bar_dp);
-                    for (int kt = 0; kt < n_kt; ++kt)
+                    if (m == 0 && it > 0) {  // the previous head's dK / dV accumulators must have been read out
+                        mbar_wait(bar_epi, (it - 1) & 1);
+                        tc_fence_after();
+                    }
+                    for (int kt = 0; kt < n_kt; ++kt) {
+                        const uint64_t pa = BT_ADV(dP_mn, kt * 32768);
+#pragma unroll 2
                         for (int k = 0; k < krows; ++k)
-                            umma_bf16(tmem_base + BT_TM_DV + kt * 64,
-                                      umma_smem_desc(sbase + BT_SM_P + kt * 32768 + k * 2048, 16384, 1024),
-                                      umma_smem_desc(ga + k * 2048, 0, 1024), id_t, (m > 0 || k > 0) ? 1u : 0u);
-                    // dS written -> dQ_m = dS_m K, dK += dS_m^T Q_m
+                            umma_bf16(tmem_base + BT_TM_DV + kt * 64, BT_ADV(pa, k * 2048), BT_ADV(gd, k * 2048), id_t,
+                                      (m > 0 || k > 0) ? 1u : 0u);
+                    }
+                    BT_TR(5 + 5 * m);
+                    // dS written -> S_{m+1}, dQ_m = dS_m K, dK += dS_m^T Q_m
                     mbar_wait(bar_ds, ph_tile);
                     tc_fence_after();
+                    BT_TR(6 + 5 * m);
+                    if (m + 1 < n_mt) issue_s(m + 1);
                     // K extent = keys actually loaded (zero-filled up to the next multiple of 16): never multiply
                     // a zero dS column with stale shared memory
-                    for (int ks = 0; ks < ((L + 15) >> 4); ++ks)
-                        umma_bf16(tmem_base + BT_TM_DQ,
-                                  umma_smem_desc(sbase + BT_SM_DS + (ks >> 2) * 16384 + (ks & 3) * 32, 0, 1024),
-                                  umma_smem_desc(sbase + BT_SM_K + ks * 2048, 0, 1024), id_dq, ks > 0 ? 1u : 0u);
-                    for (int kt = 0; kt < n_kt; ++kt)
+#pragma unroll 2
+                    for (int ks = 0; ks < ksteps; ++ks)
+                        umma_bf16(tmem_base + BT_TM_DQ, BT_ADV(dDS_k, (ks >> 2) * 16384 + (ks & 3) * 32),
+                                  BT_ADV(dK_kmaj, ks * 2048), id_dq, ks > 0 ? 1u : 0u);
+                    umma_commit(bar_dq);
+                    for (int kt = 0; kt < n_kt; ++kt) {
+                        const uint64_t da = BT_ADV(dDS_mn, kt * 32768);
+#pragma unroll 2
                         for (int k = 0; k < krows; ++k)
-                            umma_bf16(tmem_base + BT_TM_DK + kt * 64,
-                                      umma_smem_desc(sbase + BT_SM_DS + kt * 32768 + k * 2048, 16384, 1024),
-                                      umma_smem_desc(qa + k * 2048, 0, 1024), id_t, (m > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(bar_dq);  // retires after everything issued so far
+                            umma_bf16(tmem_base + BT_TM_DK + kt * 64, BT_ADV(da, k * 2048), BT_ADV(qd, k * 2048), id_t,
+                                      (m > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(bar_free);
+                    BT_TR(7 + 5 * m);
+                    if (m == n_mt - 1) {  // operands free once every product of this head has retired
+                        mbar_wait(bar_free, ph_tile);
+                        if (head + (int)gridDim.x < heads_total) load_head(head + gridDim.x);
+                        BT_TR(13);
+                    }
                     ph_tile ^= 1;
                 }
             }
+#undef BT_ADV
         }
         __syncwarp();
     } else {
         // ================================================================ row threads
+        // 512 threads: four per query row, each owning a quarter of the key columns in 16-column units
+        // (3 + 3 + 2 + 2 of the 10 units), so every phase between two barriers is short.
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
         const int rt = tid & 127;        // row inside the 128-row tile
-        const int half = tid >> 7;       // 0: key chunks 0..2 (dK rows), 1: key chunks 3..4 (dV rows)
-        const int c_lo = half ? 3 : 0, c_hi = half ? BT_NK / 32 : 3;
+        const int qtr = tid >> 7;        // column quarter
+        const int u_lo = qtr == 0 ? 0 : (qtr == 1 ? 3 : (qtr == 2 ? 6 : 8));
+        const int u_hi = qtr == 0 ? 3 : (qtr == 1 ? 6 : (qtr == 2 ? 8 : 10));
         const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+        const uint32_t drop_thr = attn_drop_threshold(p.drop_p);
         const bf16* dout = reinterpret_cast<const bf16*>(p.dout);
         const bf16* outp = reinterpret_cast<const bf16*>(p.out);
         bf16* dqkv = reinterpret_cast<bf16*>(p.dqkv);
+        const float scale2 = p.sm_scale * LOG2E;
         uint32_t it = 0, ph_s = 0, ph_dp = 0, ph_dq = 0;
+        uint32_t tiles_done = 0;  // row tiles finished by this CTA (bar_free completes once per tile)
+        // token position (thread j < 160) and row lse of the NEXT head are fetched one head ahead
+        float nx_pos = 0.f, nx_lse0 = 0.f, nx_lse1 = 0.f;
+        auto prefetch_head = [&](int head) {
+            if (head >= heads_total) return;
+            const int b = head / p.H;
+            if (tid < BT_NK) nx_pos = tid < L ? (float)(p.pos != nullptr ? p.pos[(long long)b * L + tid] : tid) : 0.f;
+            nx_lse0 = rt < L ? p.lse[(long long)head * L + rt] * LOG2E : 0.f;
+            nx_lse1 = (n_mt > 1 && 128 + rt < L) ? p.lse[(long long)head * L + 128 + rt] * LOG2E : 0.f;
+        };
+        prefetch_head(blockIdx.x);
         for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
             const int b = head / p.H, h = head - b * p.H;
             const long long bh = head;
             const float coef = head_coef(p, h);
+            const float coef2 = coef * LOG2E;
             float dc_part = 0.f;
-            for (int j = tid; j < BT_NK; j += BT_ROWT)
-                s_pos[j] = j < L ? (p.pos != nullptr ? p.pos[(long long)b * L + j] : j) : 0;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int m = 0; m < n_mt; ++m) {
-                const int i = m * 128 + rt;           // query row
-                const bool row_ok = i < L;
-                const bool row_used = m == 0 || rt < 32;   // rows inside the K extent of this tile
-                float delta = 0.f, lse_i = 0.f;
-                int pos_i = 0;
-                if (row_ok) {
-                    const bf16* go = dout + ((long long)b * L + i) * D + h * HD;
-                    const bf16* oo = outp + ((long long)b * L + i) * D + h * HD;
+            if (tid == 0) BT_TR(16);
+            if (tid < BT_NK) s_pos[tid] = nx_pos;
+            const float lse_m[2] = {nx_lse0, nx_lse1};
+            prefetch_head(head + gridDim.x);
+            // delta_i = dO_i . O_i of both row tiles from the TMA-staged tiles (each thread: its 16 of the 64 dims)
+            mbar_wait(bar_load, it & 1);
+            float delta_m[2] = {0.f, 0.f};
 #pragma unroll
-                    for (int d = 0; d < HD; d += 8) {
-                        const uint4 a = *reinterpret_cast<const uint4*>(go + d);
-                        const uint4 c = *reinterpret_cast<const uint4*>(oo + d);
+            for (int m = 0; m < 2; ++m) {
+                if (m < n_mt && (m == 0 || rt < 32)) {
+                    const uint8_t* gt = smem + BT_SM_DO + m * 16384 + rt * 128;
+                    const uint8_t* ot = smem + BT_SM_O + m * 16384 + rt * 128;
+                    float d = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int unit = (qtr * 2 + k) ^ (rt & 7);
+                        const uint4 a = *reinterpret_cast<const uint4*>(gt + unit * 16);
+                        const uint4 c = *reinterpret_cast<const uint4*>(ot + unit * 16);
                         const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), a2 = unpack_bf16x2(a.z),
                                      a3 = unpack_bf16x2(a.w);
                         const float2 c0 = unpack_bf16x2(c.x), c1 = unpack_bf16x2(c.y), c2 = unpack_bf16x2(c.z),
                                      c3 = unpack_bf16x2(c.w);
-                        delta += a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y + a2.x * c2.x + a2.y * c2.y +
-                                 a3.x * c3.x + a3.y * c3.y;
+                        d += a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y + a2.x * c2.x + a2.y * c2.y +
+                             a3.x * c3.x + a3.y * c3.y;
                     }
-                    lse_i = p.lse[bh * L + i] * LOG2E;
-                    pos_i = s_pos[i];
+                    delta_m[m] = d;  // quarter of the dot product; the four quarters meet in shared memory
                 }
-                const float scale2 = p.sm_scale * LOG2E, coef2 = coef * LOG2E;
+            }
+            s_delta[qtr][rt] = delta_m[0];
+            if (rt < 32) s_delta[qtr][128 + rt] = delta_m[1];
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+            delta_m[0] = s_delta[0][rt] + s_delta[1][rt] + s_delta[2][rt] + s_delta[3][rt];
+            {
+                const int r1 = 128 + (rt & 31);
+                delta_m[1] = s_delta[0][r1] + s_delta[1][r1] + s_delta[2][r1] + s_delta[3][r1];
+            }
+            if (tid == 0) BT_TR(17);
+            for (int m = 0; m < n_mt; ++m) {
+                const int i = m * 128 + rt;           // query row
+                const bool row_ok = i < L;
+                const bool row_used = m == 0 || rt < 32;   // rows inside the K extent of this tile
+                const float delta = delta_m[m], lse_i = lse_m[m];
+                const float fpos_i = row_ok ? s_pos[i] : 0.f;
                 uint8_t* prow = smem + BT_SM_P + rt * 128;
                 uint8_t* drow = smem + BT_SM_DS + rt * 128;
-                uint32_t keepbits[2] = {0xffffffffu, 0xffffffffu};  // dropout keep flags of this thread's <= 3 chunks... (see below)
-                uint32_t keepbits2 = 0xffffffffu;
+                uint32_t keepbits[3] = {0xffffu, 0xffffu, 0xffffu};  // dropout keep flags of this thread's <= 3 units
 
                 // ---- P (undropped, parked in the dS buffer) and Pd (dropout applied) from S
+                if (tid == 0) BT_TR(18 + 8 * m);
                 mbar_wait(bar_s, ph_s);
                 ph_s ^= 1;
                 tc_fence_after();
+                if (tid == 0) BT_TR(19 + 8 * m);
+                if (tiles_done > 0) mbar_wait(bar_free, (tiles_done - 1) & 1);  // P / dS buffers of the previous tile
+                if (row_used) {
+                    const uint32_t row_key = DROP ? attn_row_key(p.seed, bh, L, i) : 0u;
+                    // rows beyond L: lse = +inf makes every probability exactly 0 without a per-element test
+                    const float nlse = row_ok ? -lse_i : -INFINITY;
 #pragma unroll 1
-                for (int c = c_lo; c < c_hi; ++c) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_S + c * 32, raw);
-                    tmem_ld_wait();
-                    if (!row_used) continue;
-                    uint32_t kb = 0;
+                    for (int uu = 0; uu < 3; ++uu) {
+                        const int u = u_lo + uu;
+                        if (u >= u_hi) break;
+                        uint32_t raw[16];
+                        tmem_ld_32x16(tmem_base + lane_off + BT_TM_S + u * 16, raw);
+                        tmem_ld_wait();
+                        const bool full_unit = u * 16 + 16 <= L;  // warp-uniform: no key of this unit is padding
+                        uint32_t kb = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float pv[8], pd[8];
+                        for (int g8 = 0; g8 < 2; ++g8) {
+                            float pv[8], pd[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int j = c * 32 + u * 8 + e;
-                            float pr = 0.f;
-                            if (row_ok && j < L) {
-                                const int pj = s_pos[j];
-                                const float t = fmaf(__uint_as_float(raw[u * 8 + e]), scale2,
-                                                     -coef2 * fabsf((float)(pos_i - pj)));
-                                pr = ex2_approx(t - lse_i);
+                            for (int g4 = 0; g4 < 2; ++g4) {
+                                const int j0 = u * 16 + g8 * 8 + g4 * 4;
+                                const float4 pj = *reinterpret_cast<const float4*>(&s_pos[j0]);
+                                const float pjs[4] = {pj.x, pj.y, pj.z, pj.w};
+                                uint32_t kf[4] = {1u, 1u, 1u, 1u};
+                                if (DROP) {
+                                    const uint2 bits = attn_bits4(row_key, j0 >> 2);
+                                    kf[0] = (bits.x & 0xffffu) >= drop_thr; kf[1] = (bits.x >> 16) >= drop_thr;
+                                    kf[2] = (bits.y & 0xffffu) >= drop_thr; kf[3] = (bits.y >> 16) >= drop_thr;
+                                }
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float t = fmaf(__uint_as_float(raw[g8 * 8 + g4 * 4 + e]), scale2, nlse);
+                                    float pr = ex2_approx(fmaf(fabsf(fpos_i - pjs[e]), -coef2, t));
+                                    if (!full_unit && j0 + e >= L) pr = 0.f;
+                                    pv[g4 * 4 + e] = pr;
+                                    pd[g4 * 4 + e] = kf[e] ? pr * inv_keep : 0.f;
+                                    if (DROP) kb |= kf[e] << (g8 * 8 + g4 * 4 + e);
+                                }
                             }
-                            pv[e] = pr;
-                            bool keep = true;
-                            if (DROP) {
-                                keep = attn_keep(p.seed, bh, L, i, j, p.drop_p);
-                                kb |= (keep ? 1u : 0u) << (u * 8 + e);
-                            }
-                            pd[e] = keep ? pr * inv_keep : 0.f;
+                            uint4 v, w;
+                            v.x = pack_bf16x2(pd[0], pd[1]); v.y = pack_bf16x2(pd[2], pd[3]);
+                            v.z = pack_bf16x2(pd[4], pd[5]); v.w = pack_bf16x2(pd[6], pd[7]);
+                            w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
+                            w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
+                            const int unit = ((u & 3) * 2 + g8) ^ (rt & 7);
+                            *reinterpret_cast<uint4*>(prow + (u >> 2) * 16384 + unit * 16) = v;
+                            *reinterpret_cast<uint4*>(drow + (u >> 2) * 16384 + unit * 16) = w;
                         }
-                        uint4 v, w;
-                        v.x = pack_bf16x2(pd[0], pd[1]); v.y = pack_bf16x2(pd[2], pd[3]);
-                        v.z = pack_bf16x2(pd[4], pd[5]); v.w = pack_bf16x2(pd[6], pd[7]);
-                        w.x = pack_bf16x2(pv[0], pv[1]); w.y = pack_bf16x2(pv[2], pv[3]);
-                        w.z = pack_bf16x2(pv[4], pv[5]); w.w = pack_bf16x2(pv[6], pv[7]);
-                        const int unit = ((c & 1) * 4 + u) ^ (rt & 7);
-                        *reinterpret_cast<uint4*>(prow + (c >> 1) * 16384 + unit * 16) = v;
-                        *reinterpret_cast<uint4*>(drow + (c >> 1) * 16384 + unit * 16) = w;
+                        if (uu == 0) keepbits[0] = kb;
+                        else if (uu == 1) keepbits[1] = kb;
+                        else keepbits[2] = kb;
                     }
-                    if (c - c_lo == 0) keepbits[0] = kb;
-                    else if (c - c_lo == 1) keepbits[1] = kb;
-                    else keepbits2 = kb;
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_p);
+                if (tid == 0) BT_TR(20 + 8 * m);
 
                 // ---- dS = P * (dP * keep - delta), d(alibi scale)
                 mbar_wait(bar_dp, ph_dp);
                 ph_dp ^= 1;
                 tc_fence_after();
+                if (tid == 0) BT_TR(21 + 8 * m);
+                if (row_used) {
 #pragma unroll 1
-                for (int c = c_lo; c < c_hi; ++c) {
-                    uint32_t raw[32];
-                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_S + c * 32, raw);
-                    tmem_ld_wait();
-                    if (!row_used) continue;
-                    const uint32_t kb = (c - c_lo == 0) ? keepbits[0] : ((c - c_lo == 1) ? keepbits[1] : keepbits2);
+                    for (int uu = 0; uu < 3; ++uu) {
+                        const int u = u_lo + uu;
+                        if (u >= u_hi) break;
+                        uint32_t raw[16];
+                        tmem_ld_32x16(tmem_base + lane_off + BT_TM_S + u * 16, raw);
+                        tmem_ld_wait();
+                        const uint32_t kb = uu == 0 ? keepbits[0] : (uu == 1 ? keepbits[1] : keepbits[2]);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int unit = ((c & 1) * 4 + u) ^ (rt & 7);
-                        uint4* slot = reinterpret_cast<uint4*>(drow + (c >> 1) * 16384 + unit * 16);
-                        const uint4 pw = *slot;
-                        const float2 p0 = unpack_bf16x2(pw.x), p1 = unpack_bf16x2(pw.y), p2 = unpack_bf16x2(pw.z),
-                                     p3 = unpack_bf16x2(pw.w);
-                        const float pr[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
-                        float ds[8];
+                        for (int g8 = 0; g8 < 2; ++g8) {
+                            const int unit = ((u & 3) * 2 + g8) ^ (rt & 7);
+                            uint4* slot = reinterpret_cast<uint4*>(drow + (u >> 2) * 16384 + unit * 16);
+                            const uint4 pw = *slot;
+                            const float2 p0 = unpack_bf16x2(pw.x), p1 = unpack_bf16x2(pw.y), p2 = unpack_bf16x2(pw.z),
+                                         p3 = unpack_bf16x2(pw.w);
+                            const float pr[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+                            float ds[8];
+                            const float4 pa = *reinterpret_cast<const float4*>(&s_pos[u * 16 + g8 * 8]);
+                            const float4 pb = *reinterpret_cast<const float4*>(&s_pos[u * 16 + g8 * 8 + 4]);
+                            const float pjs[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int j = c * 32 + u * 8 + e;
-                            float dp = __uint_as_float(raw[u * 8 + e]);
-                            if (DROP) dp = ((kb >> (u * 8 + e)) & 1u) ? dp * inv_keep : 0.f;
-                            ds[e] = (row_ok && j < L) ? pr[e] * (dp - delta) : 0.f;
-                            if (row_ok && j < L) dc_part -= ds[e] * fabsf((float)(pos_i - s_pos[j]));
+                            for (int e = 0; e < 8; ++e) {
+                                float dp = __uint_as_float(raw[g8 * 8 + e]);
+                                if (DROP) dp = ((kb >> (g8 * 8 + e)) & 1u) ? dp * inv_keep : 0.f;
+                                // P is exactly 0 for rows / keys beyond L, so dS is too
+                                ds[e] = pr[e] * (dp - delta);
+                                dc_part = fmaf(-ds[e], fabsf(fpos_i - pjs[e]), dc_part);
+                            }
+                            uint4 v;
+                            v.x = pack_bf16x2(ds[0], ds[1]); v.y = pack_bf16x2(ds[2], ds[3]);
+                            v.z = pack_bf16x2(ds[4], ds[5]); v.w = pack_bf16x2(ds[6], ds[7]);
+                            *slot = v;
                         }
-                        uint4 v;
-                        v.x = pack_bf16x2(ds[0], ds[1]); v.y = pack_bf16x2(ds[2], ds[3]);
-                        v.z = pack_bf16x2(ds[4], ds[5]); v.w = pack_bf16x2(ds[6], ds[7]);
-                        *slot = v;
                     }
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_ds);
+                if (tid == 0) BT_TR(22 + 8 * m);
 
-                // ---- dQ rows of this tile (also: every MMA that reads P / dS has retired)
+                // ---- dQ rows of this tile
                 mbar_wait(bar_dq, ph_dq);
                 ph_dq ^= 1;
                 tc_fence_after();
-                {
-                    const int c = half;
-                    uint32_t raw[32];
-                    tmem_ld_32x32(tmem_base + lane_off + BT_TM_DQ + c * 32, raw);
+                if (tid == 0) BT_TR(23 + 8 * m);
+                if (row_used) {
+                    uint32_t raw[16];
+                    tmem_ld_32x16(tmem_base + lane_off + BT_TM_DQ + qtr * 16, raw);
                     tmem_ld_wait();
                     if (row_ok) {
-                        bf16* o = dqkv + ((long long)b * L + i) * 3 * D + h * HD + c * 32;
+                        bf16* o = dqkv + ((long long)b * L + i) * 3 * D + h * HD + qtr * 16;
 #pragma unroll
-                        for (int d = 0; d < 32; d += 4) {
-                            float v[4] = {__uint_as_float(raw[d]) * p.sm_scale, __uint_as_float(raw[d + 1]) * p.sm_scale,
-                                          __uint_as_float(raw[d + 2]) * p.sm_scale, __uint_as_float(raw[d + 3]) * p.sm_scale};
-                            store4(o + d, v);
+                        for (int d = 0; d < 16; d += 8) {
+                            uint4 v;
+                            v.x = pack_bf16x2(__uint_as_float(raw[d]) * p.sm_scale, __uint_as_float(raw[d + 1]) * p.sm_scale);
+                            v.y = pack_bf16x2(__uint_as_float(raw[d + 2]) * p.sm_scale, __uint_as_float(raw[d + 3]) * p.sm_scale);
+                            v.z = pack_bf16x2(__uint_as_float(raw[d + 4]) * p.sm_scale, __uint_as_float(raw[d + 5]) * p.sm_scale);
+                            v.w = pack_bf16x2(__uint_as_float(raw[d + 6]) * p.sm_scale, __uint_as_float(raw[d + 7]) * p.sm_scale);
+                            *reinterpret_cast<uint4*>(o + d) = v;
                         }
                     }
                 }
                 tc_fence_before();
+                if (tid == 0) BT_TR(24 + 8 * m);
+                ++tiles_done;
             }
-            // ---- dK, dV rows (key tile kt, row tid)
-            for (int kt = 0; kt < n_kt; ++kt) {
+            // ---- dK, dV rows: quarter -> (dK | dV, key tile); final once the last tile's products retired
+            mbar_wait(bar_free, (tiles_done - 1) & 1);
+            tc_fence_after();
+            if (tid == 0) BT_TR(39);
+            {
+                const int which = qtr & 1, kt = qtr >> 1;
                 const int j = kt * 128 + rt;
-                {
-                    const int which = half;
+                if (kt < n_kt && (kt == 0 || rt < 32)) {
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         uint32_t raw[32];
@@ -835,10 +980,13 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                             const float sc = which == 0 ? p.sm_scale : 1.0f;
                             bf16* o = dqkv + ((long long)b * L + j) * 3 * D + (which + 1) * D + h * HD + c * 32;
 #pragma unroll
-                            for (int d = 0; d < 32; d += 4) {
-                                float v[4] = {__uint_as_float(raw[d]) * sc, __uint_as_float(raw[d + 1]) * sc,
-                                              __uint_as_float(raw[d + 2]) * sc, __uint_as_float(raw[d + 3]) * sc};
-                                store4(o + d, v);
+                            for (int d = 0; d < 32; d += 8) {
+                                uint4 v;
+                                v.x = pack_bf16x2(__uint_as_float(raw[d]) * sc, __uint_as_float(raw[d + 1]) * sc);
+                                v.y = pack_bf16x2(__uint_as_float(raw[d + 2]) * sc, __uint_as_float(raw[d + 3]) * sc);
+                                v.z = pack_bf16x2(__uint_as_float(raw[d + 4]) * sc, __uint_as_float(raw[d + 5]) * sc);
+                                v.w = pack_bf16x2(__uint_as_float(raw[d + 6]) * sc, __uint_as_float(raw[d + 7]) * sc);
+                                *reinterpret_cast<uint4*>(o + d) = v;
                             }
                         }
                     }
@@ -846,6 +994,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             }
             tc_fence_before();
             mbar_arrive(bar_epi);
+            if (tid == 0) BT_TR(40);
             // d(alibi_scale[h]) += slope_h * sum(-dS * dist)  (only where the clamped scale is active)
             dc_part = warp_sum(dc_part);
             if (lane == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr &&
@@ -855,7 +1004,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == BT_CTRL_WARP) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
     }
@@ -995,6 +1144,12 @@ static int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
 
 using namespace a2v;
 
+#ifdef A2V_ATTN_TRACE
+extern "C" int a2v_debug_attn_trace(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_bt_trace, sizeof(long long) * (size_t)(n < 64 ? n : 64));
+}
+#endif
+
 extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     AttnParams p;
     int rc = validate_attn(d, p);
@@ -1087,8 +1242,10 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     }
     A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dout) & 15) == 0,
                 "attention backward: qkv / dout not 16-byte aligned");
-    CUtensorMap maps[4];
-    for (int i = 0; i < 4; ++i) {
+    A2V_REQUIRE(d->out != nullptr && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+                "attention backward: forward output missing or not 16-byte aligned");
+    CUtensorMap maps[6];  // qkv (128 / 32-row boxes), dout, out
+    for (int i = 0; i < 6; ++i) {
         const bool is_q = i < 2;
         const int cols = is_q ? 3 * p.D : p.D;
         cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)p.L, (cuuint64_t)p.batch};
@@ -1096,7 +1253,7 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         cuuint32_t box[3] = {64, (cuuint32_t)((i & 1) ? 32 : 128), 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = encode(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                            const_cast<void*>(is_q ? p.qkv : p.dout), dims, strides, box, estr,
+                            const_cast<void*>(is_q ? p.qkv : (i < 4 ? p.dout : (const void*)p.out)), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
@@ -1120,8 +1277,8 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     const int heads = p.batch * p.H;
     const int grid = heads < a2v_num_sms() ? heads : a2v_num_sms();
     if (p.drop_p > 0.f)
-        attn_bwd_tcgen05_kernel<true><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+        attn_bwd_tcgen05_kernel<true><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
     else
-        attn_bwd_tcgen05_kernel<false><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], p);
+        attn_bwd_tcgen05_kernel<false><<<grid, BT_THREADS, BT_SMEM_TOTAL, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
     return a2v_check_launch("attn_bwd_tcgen05");
 }
