@@ -371,7 +371,7 @@ class PretrainEngine:
         from torch's CPU generator in the reference's order: one uniform_ for r, then one randperm."""
         cfg = self.cfg
         r = float(torch.FloatTensor(1).uniform_(max(1e-6, cfg.source_mixup), 1).item())
-        perm = torch.randperm(x.size(0)).to(torch.int32).to(self.device)
+        perm = ops.h2d_async(torch.randperm(x.size(0)).to(torch.int32), self.device)
         gain = ops.mixup_gain(x, self.hann, self.aweight, self.n_fft, self.n_fft // 2)
         mixed, _ = ops.mixup_apply(x, perm, gain, r)
         return mixed
@@ -525,7 +525,7 @@ class PretrainEngine:
         R = B * M
         assert mask.shape == (R, T)
         tk = int(T - mask[0].sum())
-        mask_u8 = torch.from_numpy(np.ascontiguousarray(mask).view(np.uint8)).to(self.device, non_blocking=True)
+        mask_u8 = ops.h2d_async(torch.from_numpy(np.ascontiguousarray(mask).view(np.uint8)), self.device)
         mi = ops.mask_index(mask_u8, tk, M)
         c.mi, c.B, c.T, c.tk, c.R = mi, B, T, tk, R
         n_masked = int(R * (T - tk))

@@ -73,6 +73,34 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+# Host -> device staging without a stream synchronisation. A copy from PAGEABLE host memory makes the
+# runtime synchronise the stream first, which stalls the launch queue once per call; small per-step host
+# values (masks, permutations, pointer tables) therefore travel through a ring of pinned buffers.
+_h2d_rings: dict = {}
+
+
+def h2d_async(src: torch.Tensor, device, slots: int = 4) -> torch.Tensor:
+    """Device copy of a CPU tensor via pinned staging (stream-ordered, never blocks on the GPU)."""
+    src = src.contiguous()
+    key = (src.dtype, src.numel(), str(device))
+    ring = _h2d_rings.get(key)
+    if ring is None:
+        ring = _h2d_rings[key] = {"buf": [None] * slots, "ev": [None] * slots, "i": 0}
+    i = ring["i"]
+    ring["i"] = (i + 1) % slots
+    if ring["buf"][i] is None:
+        ring["buf"][i] = torch.empty(src.numel(), dtype=src.dtype).pin_memory()
+    else:
+        ring["ev"][i].synchronize()  # the copy that last used this slot (several steps ago) has completed
+    buf = ring["buf"][i]
+    buf.copy_(src.view(-1))
+    out = buf.to(device, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(device))
+    ring["ev"][i] = ev
+    return out.view(src.shape)
+
+
 def _call(name: str, anchor: torch.Tensor, *args) -> None:
     L.require_device(anchor)
     fn = getattr(L.load(), name)
@@ -239,7 +267,7 @@ def make_targets(layers: Sequence[torch.Tensor], eps: float = 1e-5) -> torch.Ten
     for x in layers:
         assert x.is_contiguous() and x.shape == layers[0].shape and x.dtype == layers[0].dtype
     dev = layers[0].device
-    ptrs = torch.tensor([x.data_ptr() for x in layers], dtype=torch.int64).to(dev, non_blocking=False)
+    ptrs = h2d_async(torch.tensor([x.data_ptr() for x in layers], dtype=torch.int64), dev)
     stats = torch.empty(k, b, d_, 2, device=dev, dtype=torch.float32)
     y = torch.empty(b, t, d_, device=dev, dtype=torch.float32)
     code = L.dtype_code(layers[0])

@@ -143,7 +143,7 @@ class PretrainTrainer:
             self.stats[0:1] += res["loss_sum"]
             self.stats[2:] += res["colstats"].view(-1)
             sample_size += res["sample_size"]
-        self.stats[1] = float(sample_size)
+        self.stats[1:2].fill_(float(sample_size))  # (item assignment of a Python float synchronises the stream)
         for lo, hi in self.tail_ranges:
             self.reducer.reduce_range(lo, hi)
         if self.reducer.enabled:
