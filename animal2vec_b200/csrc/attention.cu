@@ -159,7 +159,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         umma_commit(bar_s);
     };
 
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         mbar_expect_tx(bar_q, 16384);
         tma_load_3d(smem + ATT_SMEM_Q, &tm, bar_q, h * HD, q0, b);
         mbar_expect_tx(&bar_k[0], 16384);
@@ -203,7 +203,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         }
         mbar_wait(bar_s, j & 1);
         tc_fence_after();
-        if (tid == 0 && j + 2 < n_kv) {  // K buffer `buf` is free: S(j) has been computed
+        if (warp == 0 && elect_one() && j + 2 < n_kv) {  // K buffer `buf` is free: S(j) has been computed
             mbar_expect_tx(&bar_k[buf], 16384);
             tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
         }
@@ -267,7 +267,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             mbar_wait(bar_o, (j - 1) & 1);
             tc_fence_after();
         }
-        if (tid == 0 && j + 1 < n_kv) {
+        if (warp == 0 && elect_one() && j + 1 < n_kv) {
             mbar_expect_tx(&bar_v[buf ^ 1], 16384);
             tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
         }
@@ -333,7 +333,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             mbar_wait(&bar_v[buf], (j >> 1) & 1);
             const uint32_t pa = smem_u32(smem + ATT_SMEM_P);
@@ -639,7 +639,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
         // S of the NEXT tile goes ahead of dQ/dK of this one, dQ is committed before the dK products so its
         // rows are stored while they run, and the operands of the next head are fetched as soon as the last
         // product of this head has retired -- before the row threads have drained dK / dV.
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tmQ128);
             tma_prefetch_desc(&tmQ32);
             tma_prefetch_desc(&tmG128);

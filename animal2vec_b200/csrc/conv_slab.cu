@@ -135,7 +135,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int ss = 0, bs = 0;
             uint32_t sphase = 0, bphase = 0;
             const int half_rows = p.slab_rows >> 1;
@@ -159,7 +159,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(CS_BLOCK_M, 64, false, false);
             int ss = 0, bs = 0, as = 0;
             uint32_t sphase = 0, bphase = 0, aphase = 0;
@@ -329,7 +329,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
     const int kb1 = min(total_kb, kb0 + per);
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -345,7 +345,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, 64, true, true);
             int stage = 0;
             uint32_t phase = 0;

@@ -75,7 +75,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -87,7 +93,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0, t1 = getattr(self, "t_begin", 0.0), getattr(self, "t_end", float("inf"))
+        for ts, ln in self.lines:
+            if not (t0 <= ts <= t1 + 0.2):  # only samples taken while the timed region ran
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -204,13 +213,15 @@ def run_b200(args):
     def timed(fn, steps, sampler=None):
         barrier()
         if sampler:
-            sampler.start()
+            sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(steps):
             fn(s)
         e1.record()
         barrier()
+        if sampler:
+            sampler.mark_end()
         clocks = sampler.stop() if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
@@ -235,12 +246,16 @@ def run_b200(args):
         loss_host.copy_(out["stats"][0:2], non_blocking=True)      # D2H of loss sum + sample size
         torch.cuda.current_stream().synchronize()
 
+    # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up: its start-up must not
+    # land inside the timed region; only samples taken inside the region are reported
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for s in range(args.warmup):
         step_resident(s)
     # ---- device-resident leg (the `value`), with per-GEMM events for the roofline entry
     L.gemm_timeline = []
     launches0 = L.launch_count
-    sampler = ClockSampler(local) if rank == 0 else None
     ms_total, clocks = timed(step_resident, args.steps, sampler)
     launches = L.launch_count - launches0
     tl, L.gemm_timeline = L.gemm_timeline, None
