@@ -88,29 +88,37 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-    const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-    const float e = __expf(-u * u);
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    const float erfa = fmaf(-pl * t, e, 1.0f);          // erf(|u|)
-    return 0.5f * x * (1.0f + copysignf(erfa, x));
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
-__device__ __forceinline__ float gelu_fast_grad(float x) {
-    const float u = fabsf(x) * 0.70710678118654752f;
-    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-    const float e = __expf(-u * u);                      // = exp(-x^2/2): shared by erf and the pdf
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    const float erfa = fmaf(-pl * t, e, 1.0f);
-    const float cdf = 0.5f * (1.0f + copysignf(erfa, x));
+// 14-instruction GELU (erfc form): y = relu(x) - |x| * erfc(|x|/sqrt2)/2.
+// h(x) = erfc(|x|/sqrt2)/2 (Abramowitz-Stegun 7.1.26, halved coefficients) and e = exp(-x^2/2)
+__device__ __forceinline__ float half_erfc(float x, float& e) {
+    const float a = fabsf(x);
+    const float t = rcp_approx(fmaf(0.23164188f, a, 1.0f));
+    e = ex2_approx_f((x * -0.72134752f) * x);
+    float pl = fmaf(0.5307027145f, t, -0.7265760135f);
+    pl = fmaf(pl, t, 0.7107068705f);
+    pl = fmaf(pl, t, -0.142248368f);
+    pl = fmaf(pl, t, 0.127414796f);
+    return (pl * t) * e;
+}
+__device__ __forceinline__ float gelu_erfc(float x) {
+    float e;
+    const float h = half_erfc(x, e);
+    return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float gelu_erfc_grad(float x) {
+    float e;
+    const float h = half_erfc(x, e);
+    const float cdf = x >= 0.f ? 1.0f - h : h;
     return fmaf(x * 0.3989422804014327f, e, cdf);
 }
+
+__device__ __forceinline__ float gelu_fast(float x) { return gelu_erfc(x); }
+__device__ __forceinline__ float gelu_fast_grad(float x) { return gelu_erfc_grad(x); }
 template <typename T> __device__ __forceinline__ float gelu_t(float x);
 template <> __device__ __forceinline__ float gelu_t<float>(float x) { return gelu_exact(x); }
 template <> __device__ __forceinline__ float gelu_t<bf16>(float x) { return gelu_fast(x); }

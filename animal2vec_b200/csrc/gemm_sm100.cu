@@ -18,7 +18,8 @@ namespace a2v {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 192;       // 2 control warps + 4 epilogue warps
+constexpr int GEMM_THREADS_WIDE = 320;  // GELU epilogues: 8 epilogue warps (two per TMEM lane quarter, half the columns each)
 
 struct GemmParams {
     int mode;
@@ -80,14 +81,16 @@ __device__ __forceinline__ void tile_k_range(const GemmParams& p, const TileCoor
     }
 }
 
-template <int BLOCK_N>
+constexpr int EPI_WIDE_PITCH = 80;  // bytes per staged bf16 row (64 + 16): conflict-free 16-byte accesses both ways
+template <int BLOCK_N, bool WIDE = false>
 struct GemmSmem {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;  // 4 epilogue warps x 32 rows x EPI_PITCH floats
+    static constexpr int EPI_BYTES = WIDE ? 8 * 32 * EPI_WIDE_PITCH   // 8 epilogue warps x 32 rows x 80 B (bf16 staging)
+                                          : 4 * 32 * 36 * 4;          // 4 epilogue warps x 32 rows x EPI_PITCH floats
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024: alignment slack
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
@@ -210,11 +213,14 @@ __device__ __forceinline__ void epilogue_chunk_f32_accum(const GemmParams& p, fl
     }
 }
 
+template <int EPI> constexpr bool epi_is_wide() { return EPI >= 0 && (EPI & EPI_GELU) != 0; }
+
 template <int BLOCK_N, int MODE, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS_WIDE, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
-    using S = GemmSmem<BLOCK_N>;
+    constexpr bool WIDE = epi_is_wide<EPI>();
+    using S = GemmSmem<BLOCK_N, WIDE>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::STAGES * S::STAGE_BYTES);
@@ -236,7 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], WIDE ? 8 : 4);
         }
         mbar_fence_init();
         fence_proxy_async();
@@ -344,7 +350,87 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
-    } else {
+    } else if (WIDE) {
+        // ------------------------------------------------------------ epilogue warps, GELU variants
+        // Eight warps: warp w reads TMEM lane quarter w % 4 and half of the tile's 32-column chunks. The
+        // arithmetic runs in the TMEM-native layout (thread = row; the bias vector is a broadcast load), the
+        // results are packed to bf16, transposed through an 80-byte-pitch staging row and leave as 16-byte
+        // stores (8 rows x 64 contiguous bytes per instruction).
+        const int q = warp & 3;
+        const int ew = warp - 2;
+        constexpr int CPW = (BLOCK_N / 32) / 2 > 0 ? (BLOCK_N / 32) / 2 : 1;  // chunks per warp
+        const int c_begin = (ew >> 2) * CPW;
+        const uint32_t st = smem_u32(reinterpret_cast<uint8_t*>(epi_stage) + ew * (32 * EPI_WIDE_PITCH));
+        const int rrow = lane & 7, rchunk = lane >> 3;  // staged read: row rrow + 8 i, 16-byte chunk rchunk
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const int row0_in_block = t.m_tile * BLOCK_M + q * 32;
+            int rows_ok = p.M - row0_in_block;
+            rows_ok = rows_ok > 32 ? 32 : rows_ok;
+            const long long row_g = (long long)t.b * p.c_batch_stride + p.c_row_off + row0_in_block;
+            const int col_base = t.g * p.c_group_stride;
+            const long long row_off0 = row_g * p.ldc;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < CPW; ++cc) {
+                const int c = c_begin + cc;
+                const int col0 = t.n_tile * BLOCK_N + c * 32;
+                if (c >= BLOCK_N / 32 || col0 >= p.N) break;
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N + c * 32, raw);
+                tmem_ld_wait();
+                float x[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + col0) + j);
+                    x[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.alpha, bv.x);
+                    x[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.alpha, bv.y);
+                    x[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.alpha, bv.z);
+                    x[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), p.alpha, bv.w);
+                }
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (pass == 0 && !(EPI & EPI_PREACT)) continue;
+                    bf16* dst = reinterpret_cast<bf16*>(pass == 0 ? p.preact : p.c);
+                    if (pass == 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) x[i] = gelu_t<bf16>(x[i]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w0 = pack_bf16x2(x[8 * j], x[8 * j + 1]), w1 = pack_bf16x2(x[8 * j + 2], x[8 * j + 3]);
+                        const uint32_t w2 = pack_bf16x2(x[8 * j + 4], x[8 * j + 5]), w3 = pack_bf16x2(x[8 * j + 6], x[8 * j + 7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + lane * EPI_WIDE_PITCH + 16 * j),
+                                     "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                                     : "memory");
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = rrow + 8 * i;
+                        uint4 v;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                     : "r"(st + r * EPI_WIDE_PITCH + 16 * rchunk)
+                                     : "memory");
+                        if (r < rows_ok)
+                            *reinterpret_cast<uint4*>(dst + row_off0 + (long long)r * p.ldc + col_base + col0 + 8 * rchunk) = v;
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+    } else if (warp < 6) {
         // ------------------------------------------------------------ epilogue warps
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         int as = 0;
@@ -506,7 +592,7 @@ static int make_map(CUtensorMap* m, const a2v_operand& o, int box_rows, const ch
 
 template <int BLOCK_N, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    using S = GemmSmem<BLOCK_N>;
+    using S = GemmSmem<BLOCK_N, epi_is_wide<EPI>()>;
     static bool configured = false;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, EPI>;
     if (!configured) {
@@ -518,7 +604,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         configured = true;
     }
     int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
-    kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+    kern<<<grid, epi_is_wide<EPI>() ? GEMM_THREADS_WIDE : GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
     return a2v_check_launch("gemm_tcgen05_kernel");
 }
 
@@ -613,6 +699,12 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         if (m == 0 || m == EPI_BIAS || m == (EPI_BIAS | EPI_GELU | EPI_PREACT) || m == (EPI_BIAS | EPI_GELU) ||
             m == EPI_DGELU || m == EPI_RES)
             epi = m;
+        // the 8-warp GELU epilogue moves whole 16-byte column groups
+        if (epi >= 0 && (epi & EPI_GELU) &&
+            (d->N % 32 != 0 || d->ldc % 8 != 0 || d->c_group_stride % 8 != 0 ||
+             (reinterpret_cast<uintptr_t>(d->c) & 15) != 0 || (reinterpret_cast<uintptr_t>(d->preact) & 15) != 0 ||
+             (reinterpret_cast<uintptr_t>(d->bias) & 15) != 0))
+            epi = -1;
     }
 #define A2V_DISPATCH(BN)                                                                              \
     (d->mode == 1 ? launch_gemm<BN, 1, -1>(ta, tb, p, st)                                             \

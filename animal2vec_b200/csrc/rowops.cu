@@ -442,34 +442,6 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p, con
 // REAL channels only (pad chunks cost no arithmetic) and GELU costs 14
 // instructions (erfc form: y = relu(x) - |x| * erfc(|x|/sqrt2)/2).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ex2_approx_f(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// h(x) = erfc(|x|/sqrt2)/2 (Abramowitz-Stegun 7.1.26, halved coefficients) and e = exp(-x^2/2)
-__device__ __forceinline__ float half_erfc(float x, float& e) {
-    const float a = fabsf(x);
-    const float t = rcp_approx(fmaf(0.23164188f, a, 1.0f));
-    e = ex2_approx_f((x * -0.72134752f) * x);
-    float pl = fmaf(0.5307027145f, t, -0.7265760135f);
-    pl = fmaf(pl, t, 0.7107068705f);
-    pl = fmaf(pl, t, -0.142248368f);
-    pl = fmaf(pl, t, 0.127414796f);
-    return (pl * t) * e;
-}
-__device__ __forceinline__ float gelu_erfc(float x) {
-    float e;
-    const float h = half_erfc(x, e);
-    return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
-}
-__device__ __forceinline__ float gelu_erfc_grad(float x) {
-    float e;
-    const float h = half_erfc(x, e);
-    const float cdf = x >= 0.f ? 1.0f - h : h;
-    return fmaf(x * 0.3989422804014327f, e, cdf);
-}
-
 struct ChunkMap {
     int cs, cr, ngroups;  // stored / real 16-byte chunks per channel group, groups per row
     __device__ __forceinline__ int stored_chunk(int r) const { return (r / cr) * cs + (r % cr); }
