@@ -628,6 +628,211 @@ __global__ void __launch_bounds__(256, 2) rowln_gelu_bwd_kernel(const RowLnParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Feature-extractor layer 0: Fp32LayerNorm(127) + PSwish over (B * 80000) rows of 128 stored channels
+// (reference nn/utils.py:1107-1117,1413-1435). A 256-byte row is too short for a warp: here a warp owns
+// FOUR consecutive rows (1 KB, two fully coalesced 16-byte loads per lane), sixteen lanes per row and
+// eight channels per lane, so a lane keeps its 8 x 4 parameters (and, backward, its 8 x 4 parameter
+// gradient accumulators) in registers for the whole kernel and the row reductions take four shuffles.
+// The next four rows are prefetched into registers while the current ones are processed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float half16_sum(float v) {  // sum over the 16 lanes that share a row
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct Row128Lane {
+    float ga[8], be[8], al[8], nb[8];  // gamma, beta, PSwish alpha, -log2(e) * PSwish beta (pads: 0)
+};
+
+__device__ __forceinline__ Row128Lane load_row128_params(const RowLnParams& p, int ch0) {
+    Row128Lane q;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch0 + j;
+        const bool real = c < p.gr;
+        q.ga[j] = real ? p.gamma[c] : 0.f;
+        q.be[j] = real ? p.beta[c] : 0.f;
+        q.al[j] = real ? p.act_alpha[c] : 0.f;
+        q.nb[j] = real ? -1.4426950408889634f * p.act_beta[c] : 0.f;
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(512, 1) rowln128_pswish_fwd_kernel(const RowLnParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const int ch0 = (lane & 15) * 8;
+    const int padj = p.gr - ch0;  // elements j >= padj of this lane are padding (>= 8: none)
+    const Row128Lane q = load_row128_params(p, ch0);
+    const float inv_c = 1.0f / (float)p.gr;
+    const long long groups = (p.rows + 3) >> 2;  // four rows per warp iteration
+    const uint4* A = reinterpret_cast<const uint4*>(p.a);
+    uint4* Y = reinterpret_cast<uint4*>(p.y);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch = [&](long long g, uint4 (&v)[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = g * 4 + 2 * h + (lane >> 4);
+            v[h] = (g < groups && row < p.rows) ? __ldg(A + g * 64 + h * 32 + lane) : zero4;
+        }
+    };
+    uint4 cur[2], nxt[2];
+    fetch(gw, cur);
+    for (long long g = gw; g < groups; g += nw) {
+        fetch(g + nw, nxt);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = g * 4 + 2 * h + (lane >> 4);
+            float z[8];
+            unpack8(cur[h], z);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += z[j];
+            const float mean = half16_sum(s) * inv_c;
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                z[j] = j < padj ? z[j] - mean : 0.f;
+                v = fmaf(z[j], z[j], v);
+            }
+            const float rstd = rsqrtf(half16_sum(v) * inv_c + p.eps);
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float n = fmaf(z[j] * rstd, q.ga[j], q.be[j]);
+                const float sg = rcp_approx(1.0f + ex2_approx_f(q.nb[j] * n));  // sigmoid(beta * n)
+                o[j] = (n * q.al[j]) * sg;
+            }
+            if (row < p.rows) {
+                Y[g * 64 + h * 32 + lane] = pack8(o);
+                if ((lane & 15) == 0) {
+                    if (p.mean != nullptr) p.mean[row] = mean;
+                    if (p.rstd != nullptr) p.rstd[row] = rstd;
+                }
+            }
+        }
+        cur[0] = nxt[0];
+        cur[1] = nxt[1];
+    }
+}
+
+__global__ void __launch_bounds__(384, 1) rowln128_pswish_bwd_kernel(const RowLnParams p) {
+    __shared__ float sred[4][128];
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    const int ch0 = (lane & 15) * 8;
+    const int padj = p.gr - ch0;
+    const Row128Lane q = load_row128_params(p, ch0);
+    const float inv_c = 1.0f / (float)p.gr;
+    const long long groups = (p.rows + 3) >> 2;
+    const uint4* A = reinterpret_cast<const uint4*>(p.a);
+    const uint4* DY = reinterpret_cast<const uint4*>(p.dy);
+    uint4* DA = reinterpret_cast<uint4*>(p.da);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < 4 * 128; i += blockDim.x) (&sred[0][0])[i] = 0.f;
+    __syncthreads();
+    float acc_g[8], acc_b[8], acc_al[8], acc_ab[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc_g[j] = acc_b[j] = acc_al[j] = acc_ab[j] = 0.f;
+    auto fetch = [&](long long g, uint4 (&va)[2], uint4 (&vg)[2], float (&mu)[2], float (&rs)[2]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = g * 4 + 2 * h + (lane >> 4);
+            const bool ok = g < groups && row < p.rows;
+            va[h] = ok ? __ldg(A + g * 64 + h * 32 + lane) : zero4;
+            vg[h] = ok ? __ldg(DY + g * 64 + h * 32 + lane) : zero4;
+            mu[h] = ok ? __ldg(p.mean + row) : 0.f;
+            rs[h] = ok ? __ldg(p.rstd + row) : 0.f;
+        }
+    };
+    uint4 ca[2], cg[2], na[2], ng[2];
+    float cm[2], cr[2], nm[2], nr[2];
+    fetch(gw, ca, cg, cm, cr);
+    for (long long g = gw; g < groups; g += nw) {
+        fetch(g + nw, na, ng, nm, nr);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long row = g * 4 + 2 * h + (lane >> 4);
+            float xh[8], gy[8];
+            unpack8(ca[h], xh);
+            unpack8(cg[h], gy);
+            const float rstd = cr[h], nmr = -cm[h] * cr[h];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[j] = j < padj ? fmaf(xh[j], rstd, nmr) : 0.f;
+                const float n = fmaf(xh[j], q.ga[j], q.be[j]);
+                const float sg = rcp_approx(1.0f + ex2_approx_f(q.nb[j] * n));
+                const float bt = q.nb[j] * -0.6931471805599453f;  // PSwish beta
+                const float t = n * sg * (1.0f - sg);             // n * sigma'
+                const float dyv = gy[j];
+                acc_al[j] = fmaf(dyv, n * sg, acc_al[j]);
+                acc_ab[j] = fmaf(dyv * q.al[j], n * t, acc_ab[j]);
+                const float dn = dyv * q.al[j] * fmaf(bt, t, sg);
+                acc_g[j] = fmaf(dn, xh[j], acc_g[j]);
+                acc_b[j] += dn;
+                gy[j] = dn * q.ga[j];
+                s1 += gy[j];
+                s2 = fmaf(gy[j], xh[j], s2);
+            }
+            s1 = half16_sum(s1) * inv_c;
+            s2 = half16_sum(s2) * inv_c;
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = j < padj ? rstd * (gy[j] - s1 - xh[j] * s2) : 0.f;
+            if (row < p.rows) DA[g * 64 + h * 32 + lane] = pack8(o);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) { ca[h] = na[h]; cg[h] = ng[h]; cm[h] = nm[h]; cr[h] = nr[h]; }
+    }
+    // lanes l and l ^ 16 own the same channels
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        acc_g[j] += __shfl_xor_sync(0xffffffffu, acc_g[j], 16);
+        acc_b[j] += __shfl_xor_sync(0xffffffffu, acc_b[j], 16);
+        acc_al[j] += __shfl_xor_sync(0xffffffffu, acc_al[j], 16);
+        acc_ab[j] += __shfl_xor_sync(0xffffffffu, acc_ab[j], 16);
+    }
+    if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sred[0][ch0 + j], acc_g[j]);
+            atomicAdd(&sred[1][ch0 + j], acc_b[j]);
+            atomicAdd(&sred[2][ch0 + j], acc_al[j]);
+            atomicAdd(&sred[3][ch0 + j], acc_ab[j]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.gr; c += blockDim.x) {
+        if (p.dgamma != nullptr) atomicAdd(p.dgamma + c, sred[0][c]);
+        if (p.dbeta != nullptr) atomicAdd(p.dbeta + c, sred[1][c]);
+        if (p.dact_alpha != nullptr) atomicAdd(p.dact_alpha + c, sred[2][c]);
+        if (p.dact_beta != nullptr) atomicAdd(p.dact_beta + c, sred[3][c]);
+    }
+}
+
+static int launch_rowln128(const RowLnParams& p, bool bwd, cudaStream_t st) {
+    if (p.C != 128 || p.gw != 128 || p.gr < 121 || p.act != 2 || p.gamma == nullptr || p.beta == nullptr ||
+        p.b != nullptr || p.post != nullptr || p.drop_out > 0.f)
+        return -1;
+    if ((reinterpret_cast<uintptr_t>(p.a) & 15) != 0) return -1;
+    if (bwd && (p.da == nullptr || p.db != nullptr || (reinterpret_cast<uintptr_t>(p.dy) & 15) != 0)) return -1;
+    const long long groups = (p.rows + 3) >> 2;
+    const int threads = bwd ? 384 : 512;  // backward: 170 registers per thread for the parameter-gradient accumulators
+    long long blocks = ceil_div64(groups, threads / 32);
+    const long long cap = a2v_num_sms();
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    if (bwd)
+        rowln128_pswish_bwd_kernel<<<grid, 384, 0, st>>>(p);
+    else
+        rowln128_pswish_fwd_kernel<<<grid, 512, 0, st>>>(p);
+    return a2v_check_launch(bwd ? "rowln_bwd(c128)" : "rowln_fwd(c128)");
+}
+
 // dispatch test + launch of the specialised kernels; returns -1 when the generic path must be used
 static int launch_rowln_fast(const RowLnParams& p, bool bwd, cudaStream_t st) {
     if (p.act != 1 || p.gamma != nullptr || p.beta != nullptr || p.b != nullptr) return -1;
@@ -791,6 +996,8 @@ extern "C" int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     if (d->dtype == A2V_BF16) {
         rc = launch_rowln_fast(p, false, st);
         if (rc >= 0) return rc;
+        rc = launch_rowln128(p, false, st);
+        if (rc >= 0) return rc;
     }
     return d->dtype == A2V_F32 ? launch_rowln<float>(p, false, st) : launch_rowln<bf16>(p, false, st);
 }
@@ -806,6 +1013,8 @@ extern "C" int a2v_rowln_bwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d->dtype == A2V_BF16) {
         rc = launch_rowln_fast(p, true, st);
+        if (rc >= 0) return rc;
+        rc = launch_rowln128(p, true, st);
         if (rc >= 0) return rc;
     }
     return d->dtype == A2V_F32 ? launch_rowln<float>(p, true, st) : launch_rowln<bf16>(p, true, st);
