@@ -80,11 +80,10 @@ __device__ __forceinline__ bool attn_keep(unsigned long long seed, long long bh,
 constexpr int ATT_SMEM_Q = 0;
 constexpr int ATT_SMEM_K = 16384;             // 2 buffers
 constexpr int ATT_SMEM_V = 16384 * 3;         // 2 buffers
-constexpr int ATT_SMEM_P = 16384 * 5;         // 2 chunks of 64 keys
-constexpr int ATT_SMEM_POS = 16384 * 7;       // 128 floats (key positions of the current tile)
+constexpr int ATT_SMEM_POS = 16384 * 5;       // 128 floats (key positions of the current tile)
 constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 512;
-// 112.6 KB: two CTAs per SM need 2 x (dynamic + 1 KB reserved) <= 228 KB, i.e. <= 113 KB each. The dynamic
-// window of a kernel without static shared memory starts 1024-aligned (checked at run time, trap otherwise).
+// 80.6 KB (the probabilities live in tensor memory, not in shared memory): two CTAs per SM. The dynamic window
+// of a kernel without static shared memory starts 1024-aligned (checked at run time, trap otherwise).
 constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximum may lag by up to 2^8
 
@@ -104,6 +103,14 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Flash-style forward. One thread per query row; per 128-key tile:
@@ -112,6 +119,13 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // O is rescaled in TMEM only when a row's maximum grows by more than 2^8 (lazy rescaling), the S MMA of
 // the next tile is issued before the softmax of this one finishes, K and V tiles have separate
 // barriers so the next K can land while V is still being consumed.
+#ifdef A2V_ATTN_TRACE
+__device__ long long g_ft_trace[64];
+#define FT_TR(k) do { if (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 1 && j == 6 && tid == 0) g_ft_trace[k] = clock64(); } while (0)
+#else
+#define FT_TR(k) do { } while (0)
+#endif
+
 template <bool HAS_POS, bool DROP, bool TRIM>
 __global__ void __launch_bounds__(128, 2)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
@@ -145,6 +159,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_s = tmem_base;        // 128 columns
     const uint32_t tmem_o = tmem_base + 128;  // 64 columns
+    const uint32_t tmem_p = tmem_base + 192;  // 64 columns: P as packed bf16 pairs, the TMEM A operand of P.V
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
     const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
@@ -201,8 +216,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             spos[tid] = kj < L ? (float)p.pos[(long long)b * L + kj] : -268435456.0f;
             __syncthreads();
         }
+        FT_TR(0);
         mbar_wait(bar_s, j & 1);
         tc_fence_after();
+        FT_TR(1);
         if (warp == 0 && elect_one() && j + 2 < n_kv) {  // K buffer `buf` is free: S(j) has been computed
             mbar_expect_tx(&bar_k[buf], 16384);
             tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
@@ -262,11 +279,34 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 }
             }
         }
+        FT_TR(2);
+        // every thread holds its scores: the S accumulator is free, so S of the NEXT tile runs on the tensor
+        // pipe while this tile's exponentials are computed (it used to be issued after P.V, leaving the CTA
+        // waiting a full MMA round trip at the top of every iteration)
+        if (j + 1 < n_kv) {
+            tc_fence_before();
+            __syncthreads();
+            if (warp == 0 && elect_one()) {
+                tc_fence_after();
+                mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                FT_TR(8);
+                issue_s(buf ^ 1);
+                FT_TR(9);
+#ifdef A2V_ATTN_TRACE
+                if (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 1 && j == 6) {
+                    while (!mbar_try_wait(bar_s, (j + 1) & 1)) {}
+                    g_ft_trace[10] = clock64();
+                }
+#endif
+            }
+        }
         // previous P.V done: P smem, V[buf^1] and the O accumulator are ours again
         if (j > 0) {
             mbar_wait(bar_o, (j - 1) & 1);
             tc_fence_after();
         }
+        FT_TR(3);
         if (warp == 0 && elect_one() && j + 1 < n_kv) {
             mbar_expect_tx(&bar_v[buf ^ 1], 16384);
             tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
@@ -289,65 +329,65 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         }
         if (grow) m_run = m_tile;
 
-        // probabilities -> shared memory (bf16, 128B-swizzled K-major A operand of P.V)
+        // probabilities -> TENSOR memory (packed bf16 pairs, 16 columns per 32 keys): the A operand of P.V is read
+        // from TMEM, so P costs no shared-memory bandwidth (S and P.V operands out of smem were the bottleneck:
+        // 144 KB per 128x128 tile against 128 B/clk)
         float l_tile = 0.f;
         const float e_off = c_row - m_run;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-            uint8_t* prow = smem + ATT_SMEM_P + (c >> 1) * 16384 + tid * 128;
             if (TRIM && !warp_active) continue;  // rows beyond L: their P rows only feed O rows that are never stored
+            uint32_t pk[16];
             if (TRIM && c * 32 >= nvalid) {      // keys beyond L: exact zeros (they sit inside the K extent of P.V)
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    *reinterpret_cast<uint4*>(prow + (((c & 1) * 4 + u) ^ (tid & 7)) * 16) = make_uint4(0u, 0u, 0u, 0u);
-                continue;
-            }
+                for (int i = 0; i < 16; ++i) pk[i] = 0u;
+            } else {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                float e[8];
+                for (int u = 0; u < 4; ++u) {
+                    float e[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    e[i] = ex2_approx(fmaf(t[c * 32 + u * 8 + i], e_mul, e_off));
-                    l_tile += e[i];
-                }
-                if (DROP) {
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const uint2 bits = attn_bits4(row_key, (k0 + c * 32 + u * 8) / 4 + g);
-                        e[4 * g + 0] = (bits.x & 0xffffu) >= drop_thr ? e[4 * g + 0] * inv_keep : 0.f;
-                        e[4 * g + 1] = (bits.x >> 16) >= drop_thr ? e[4 * g + 1] * inv_keep : 0.f;
-                        e[4 * g + 2] = (bits.y & 0xffffu) >= drop_thr ? e[4 * g + 2] * inv_keep : 0.f;
-                        e[4 * g + 3] = (bits.y >> 16) >= drop_thr ? e[4 * g + 3] * inv_keep : 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                        e[i] = ex2_approx(fmaf(t[c * 32 + u * 8 + i], e_mul, e_off));
+                        l_tile += e[i];
                     }
+                    if (DROP) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const uint2 bits = attn_bits4(row_key, (k0 + c * 32 + u * 8) / 4 + g);
+                            e[4 * g + 0] = (bits.x & 0xffffu) >= drop_thr ? e[4 * g + 0] * inv_keep : 0.f;
+                            e[4 * g + 1] = (bits.x >> 16) >= drop_thr ? e[4 * g + 1] * inv_keep : 0.f;
+                            e[4 * g + 2] = (bits.y & 0xffffu) >= drop_thr ? e[4 * g + 2] * inv_keep : 0.f;
+                            e[4 * g + 3] = (bits.y >> 16) >= drop_thr ? e[4 * g + 3] * inv_keep : 0.f;
+                        }
+                    }
+                    pk[u * 4 + 0] = pack_bf16x2(e[0], e[1]);
+                    pk[u * 4 + 1] = pack_bf16x2(e[2], e[3]);
+                    pk[u * 4 + 2] = pack_bf16x2(e[4], e[5]);
+                    pk[u * 4 + 3] = pack_bf16x2(e[6], e[7]);
                 }
-                uint4 v;
-                v.x = pack_bf16x2(e[0], e[1]);
-                v.y = pack_bf16x2(e[2], e[3]);
-                v.z = pack_bf16x2(e[4], e[5]);
-                v.w = pack_bf16x2(e[6], e[7]);
-                const int unit = ((c & 1) * 4 + u) ^ (tid & 7);
-                *reinterpret_cast<uint4*>(prow + unit * 16) = v;
             }
+            tmem_st_32x16(tmem_p + lane_off + c * 16, pk);
         }
+        tmem_st_wait();
         l_run += l_tile;
-        fence_proxy_async();
+        FT_TR(4);
         tc_fence_before();
         __syncthreads();
+        FT_TR(5);
         if (warp == 0 && elect_one()) {
             tc_fence_after();
+            FT_TR(11);
             mbar_wait(&bar_v[buf], (j >> 1) & 1);
-            const uint32_t pa = smem_u32(smem + ATT_SMEM_P);
+            FT_TR(12);
             const uint32_t va = smem_u32(smem + ATT_SMEM_V + buf * 16384);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                umma_bf16(tmem_o, umma_smem_desc(pa + (k >> 2) * 16384 + (k & 3) * 32, 0, 1024),
-                          umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k)  // 16 keys = 8 packed columns of P per step
+                umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o,
+                             (j > 0 || k > 0) ? 1u : 0u);
             umma_commit(bar_o);
-            if (j + 1 < n_kv) {  // S of the next tile: every thread has its scores in registers by now
-                mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
-                issue_s(buf ^ 1);
-            }
+            FT_TR(13);
         }
+        FT_TR(6);
     }
 
     mbar_wait(bar_o, (n_kv - 1) & 1);
@@ -1147,6 +1187,9 @@ using namespace a2v;
 #ifdef A2V_ATTN_TRACE
 extern "C" int a2v_debug_attn_trace(long long* out, int n) {
     return (int)cudaMemcpyFromSymbol(out, g_bt_trace, sizeof(long long) * (size_t)(n < 64 ? n : 64));
+}
+extern "C" int a2v_debug_attn_fwd_trace(long long* out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_ft_trace, sizeof(long long) * (size_t)(n < 64 ? n : 64));
 }
 #endif
 
