@@ -91,7 +91,10 @@ struct GemmSmem {
     static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
     static constexpr int EPI_BYTES = WIDE ? 8 * 32 * EPI_WIDE_PITCH   // 8 epilogue warps x 32 rows x 80 B (bf16 staging)
                                           : 4 * 32 * 36 * 4;          // 4 epilogue warps x 32 rows x EPI_PITCH floats
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024: alignment slack
+    // per-tile bias vector staged per epilogue warp BEFORE it waits for the accumulator (a global load inside the
+    // chunk loop costs a full memory latency per 32-column chunk, which a K = 1024 tile cannot hide)
+    static constexpr int BIAS_BYTES = WIDE ? 8 * (BLOCK_N / 2) * 4 : 4 * BLOCK_N * 4;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + BIAS_BYTES + 1024;  // +1024: alignment slack
     static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
 };
 
@@ -130,14 +133,17 @@ template <int EPI> __device__ __forceinline__ bool epi_res(const GemmParams& p) 
 
 template <typename TC, int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, float (&v)[32], long long row_off0, int rows_ok,
-                                               int gcol, int cols_ok, int lane) {
+                                               int gcol, int cols_ok, int lane, const float* bias_s = nullptr) {
     // row_off0: element offset of the warp's first row; rows_ok: number of valid rows (<= 32) from it;
     // gcol: global column of this lane's first element; cols_ok: valid columns from gcol (may be <= 0)
     const int rsub = lane >> 3;
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
     const bool full = cols_ok >= 4;
     if (epi_bias<EPI>(p) && cols_ok > 0) {
-        if (full) {
+        if (bias_s != nullptr) {  // staged per tile in shared memory (pads are zeros)
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s);
+            bias[0] = b4.x; bias[1] = b4.y; bias[2] = b4.z; bias[3] = b4.w;
+        } else if (full) {
             load4(p.bias + gcol, bias);
         } else {
 #pragma unroll
@@ -229,6 +235,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* epi_stage = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES);
+    float* bias_stage = reinterpret_cast<float*>(smem + S::STAGES * S::STAGE_BYTES + S::BAR_BYTES + S::EPI_BYTES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -372,6 +379,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const long long row_g = (long long)t.b * p.c_batch_stride + p.c_row_off + row0_in_block;
             const int col_base = t.g * p.c_group_stride;
             const long long row_off0 = row_g * p.ldc;
+            float* bs = bias_stage + ew * (CPW * 32);  // this warp's CPW chunks of the tile's bias vector
+            {
+                const int cbase = t.n_tile * BLOCK_N + c_begin * 32;
+                const float* bg = p.bias + col_base + cbase;
+                const int ncols = p.N - cbase;
+                for (int j = lane * 4; j < CPW * 32; j += 128) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j + 4 <= ncols) b4 = __ldg(reinterpret_cast<const float4*>(bg + j));
+                    *reinterpret_cast<float4*>(bs + j) = b4;
+                }
+                __syncwarp();
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
 #pragma unroll 1
@@ -385,7 +404,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col_base + col0) + j);
+                    const float4 bv = *reinterpret_cast<const float4*>(bs + cc * 32 + 4 * j);
                     x[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.alpha, bv.x);
                     x[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.alpha, bv.y);
                     x[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.alpha, bv.z);
@@ -472,6 +491,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                 }
             }
+            constexpr bool STAGE_BIAS = EPI >= 0 && (EPI & EPI_BIAS) != 0;
+            float* bs = bias_stage + (warp - 2) * BLOCK_N;
+            if (STAGE_BIAS) {
+                const float* bg = p.bias + col_base + t.n_tile * BLOCK_N;
+                const int ncols = p.N - t.n_tile * BLOCK_N;
+#pragma unroll
+                for (int j = lane * 4; j < BLOCK_N; j += 128) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j + 4 <= ncols) b4 = __ldg(reinterpret_cast<const float4*>(bg + j));
+                    else {
+                        if (j < ncols) b4.x = bg[j];
+                        if (j + 1 < ncols) b4.y = bg[j + 1];
+                        if (j + 2 < ncols) b4.z = bg[j + 2];
+                    }
+                    *reinterpret_cast<float4*>(bs + j) = b4;
+                }
+                __syncwarp();
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
 #pragma unroll(PREFETCH ? BLOCK_N / 32 : 1)
@@ -513,7 +550,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         q0.alpha = 1.0f;
                         epilogue_chunk<bf16, 0>(q0, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     } else if (EPI >= 0) {
-                        epilogue_chunk<bf16, EPI>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
+                        epilogue_chunk<bf16, EPI>(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane,
+                                                  STAGE_BIAS ? bs + c * 32 + (lane & 7) * 4 : nullptr);
                     } else if (p.out_atomic || p.out_accumulate) {
                         epilogue_chunk_f32_accum(p, v, row_off0, rows_ok, col_base + lcol, cols_ok, lane);
                     } else if (p.c_f32) {
@@ -706,6 +744,9 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
              (reinterpret_cast<uintptr_t>(d->bias) & 15) != 0))
             epi = -1;
     }
+    // staged bias vectors are read with 16-byte loads
+    if (epi >= 0 && (epi & EPI_BIAS) && ((reinterpret_cast<uintptr_t>(d->bias) & 15) != 0 || d->c_group_stride % 4 != 0))
+        epi = -1;
 #define A2V_DISPATCH(BN)                                                                              \
     (d->mode == 1 ? launch_gemm<BN, 1, -1>(ta, tb, p, st)                                             \
      : epi == 0 ? launch_gemm<BN, 0, 0>(ta, tb, p, st)                                                \

@@ -833,6 +833,317 @@ static int launch_rowln128(const RowLnParams& p, bool bwd, cudaStream_t st) {
     return a2v_check_launch(bwd ? "rowln_bwd(c128)" : "rowln_fwd(c128)");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Specialised bf16 kernels for the post-LN residual norms of AltBlock (reference nn/modalities/modules.py:
+// 329-333: x = LN1(x + drop(attn)), x = LN2(r + drop(mlp))) and BlockEncoder's first norm without a second
+// operand: y = LN(a + dropout_b(b)) * gamma + beta over rows of NV*256 contiguous channels. 96 launches
+// forward and 48 backward per step at the large config. Everything is resolved at compile time; a lane
+// owns NV 16-byte chunks; the backward keeps gamma and the three column accumulators (dgamma, dbeta and
+// the column sum of db = the bias gradient of the Linear that produced b) in registers for the whole
+// kernel, and the dropout keep flags of a row in ONE 32-bit register (hashed once, used for z and for db).
+// Dropout indexing is the generic kernels' (one 64-bit hash per 4 consecutive channels).
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ unsigned res_keep_bits(unsigned long long seed, long long row, int C, const int (&off)[NV],
+                                                  float drop) {
+    unsigned bits = 0;
+    const uint32_t thr = (uint32_t)(drop * 65536.0f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const unsigned long long idx4 = (unsigned long long)(row * C + (off[i] >> 1)) >> 2;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t h = rng64(seed, idx4 + hh);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (((uint32_t)(h >> (16 * j)) & 0xffffu) >= thr) bits |= 1u << (8 * i + 4 * hh + j);
+        }
+    }
+    return bits;
+}
+
+template <int NV, bool HAS_B, bool DROP>
+__global__ void __launch_bounds__(256, 2) resln_fwd_kernel(const RowLnParams p, const int stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NTENS = HAS_B ? 2 : 1;
+    constexpr int C = NV * 256;
+    constexpr int row_bytes = C * 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
+    float* tab = reinterpret_cast<float*>(smem_raw);  // [gamma | beta] x C
+    unsigned char* rings = smem_raw + 2 * C * sizeof(float);
+    unsigned char* ring = rings + (size_t)warp * stages * NTENS * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rings + (size_t)ROWLN_WARPS * stages * NTENS * row_bytes) + warp * FAST_STAGES_MAX;
+    const unsigned char* src[NTENS];
+    src[0] = reinterpret_cast<const unsigned char*>(p.a);
+    if (HAS_B) src[NTENS - 1] = reinterpret_cast<const unsigned char*>(p.b);
+    int off[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) off[i] = (lane + 32 * i) * 16;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        tab[c] = p.gamma[c];
+        tab[C + c] = p.beta != nullptr ? p.beta[c] : 0.f;
+    }
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    for (int s = 0; s < stages; ++s)
+        fast_issue<NTENS>(ring + (size_t)s * NTENS * row_bytes, &bars[s], src, warp0 + (long long)s * nwarps, p.rows, row_bytes, lane);
+    const float inv_c = 1.0f / (float)C;
+    const float keep_b = DROP ? 1.0f / (1.0f - p.drop_b) : 1.0f;
+    unsigned char* Y = reinterpret_cast<unsigned char*>(p.y);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        unsigned keep = 0xffffffffu;
+        if (HAS_B && DROP) keep = res_keep_bits<NV>(p.seed_b, row, C, off, p.drop_b);  // before the wait: overlaps the copy
+        mbar_wait(&bars[slot], (uint32_t)((it / stages) & 1));
+        const unsigned char* sm = ring + (size_t)slot * NTENS * row_bytes;
+        uint4 va[NV], vb[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            va[i] = *reinterpret_cast<const uint4*>(sm + off[i]);
+            if (HAS_B) vb[i] = *reinterpret_cast<const uint4*>(sm + row_bytes + off[i]);
+        }
+        __syncwarp();
+        fast_issue<NTENS>(ring + (size_t)slot * NTENS * row_bytes, &bars[slot], src, row + (long long)stages * nwarps, p.rows,
+                          row_bytes, lane);
+        float z[NV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            unpack8(va[i], z[i]);
+            if (HAS_B) {
+                float t[8];
+                unpack8(vb[i], t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (DROP) t[j] = ((keep >> (8 * i + j)) & 1u) ? t[j] * keep_b : 0.f;
+                    z[i][j] += t[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += z[i][j];
+        }
+        const float mean = warp_sum(s) * inv_c;
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                z[i][j] -= mean;
+                v = fmaf(z[i][j], z[i][j], v);
+            }
+        const float rstd = rsqrtf(warp_sum(v) * inv_c + p.eps);
+        if (lane == 0) {
+            if (p.mean != nullptr) p.mean[row] = mean;
+            if (p.rstd != nullptr) p.rstd[row] = rstd;
+        }
+        unsigned char* yrow = Y + row * row_bytes;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float o[8];
+            const float4 g0 = *reinterpret_cast<const float4*>(tab + (off[i] >> 1));
+            const float4 g1 = *reinterpret_cast<const float4*>(tab + (off[i] >> 1) + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(tab + C + (off[i] >> 1));
+            const float4 b1 = *reinterpret_cast<const float4*>(tab + C + (off[i] >> 1) + 4);
+            o[0] = fmaf(z[i][0] * rstd, g0.x, b0.x); o[1] = fmaf(z[i][1] * rstd, g0.y, b0.y);
+            o[2] = fmaf(z[i][2] * rstd, g0.z, b0.z); o[3] = fmaf(z[i][3] * rstd, g0.w, b0.w);
+            o[4] = fmaf(z[i][4] * rstd, g1.x, b1.x); o[5] = fmaf(z[i][5] * rstd, g1.y, b1.y);
+            o[6] = fmaf(z[i][6] * rstd, g1.z, b1.z); o[7] = fmaf(z[i][7] * rstd, g1.w, b1.w);
+            *reinterpret_cast<uint4*>(yrow + off[i]) = pack8(o);
+        }
+    }
+}
+
+// backward: da = dLN(dy * gamma); db = dropout_b-masked da; dgamma += sum dy*xhat, dbeta += sum dy, dbias_b += sum db
+template <int NV, bool HAS_B, bool DROP>
+__global__ void __launch_bounds__(256, 1) resln_bwd_kernel(const RowLnParams p, const int stages, float* dbias_b) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int NTENS = HAS_B ? 3 : 2;
+    constexpr int C = NV * 256;
+    constexpr int row_bytes = C * 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + warp;
+    const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
+    unsigned char* ring = smem_raw + (size_t)warp * stages * NTENS * row_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ROWLN_WARPS * stages * NTENS * row_bytes) + warp * FAST_STAGES_MAX;
+    const unsigned char* src[NTENS];
+    src[0] = reinterpret_cast<const unsigned char*>(p.a);
+    src[1] = reinterpret_cast<const unsigned char*>(p.dy);
+    if (HAS_B) src[NTENS - 1] = reinterpret_cast<const unsigned char*>(p.b);
+    int off[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) off[i] = (lane + 32 * i) * 16;
+    float ga[NV][8], acc_g[NV][8], acc_b[NV][8], acc_s[HAS_B ? NV : 1][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g0 = *reinterpret_cast<const float4*>(p.gamma + (off[i] >> 1));
+        const float4 g1 = *reinterpret_cast<const float4*>(p.gamma + (off[i] >> 1) + 4);
+        ga[i][0] = g0.x; ga[i][1] = g0.y; ga[i][2] = g0.z; ga[i][3] = g0.w;
+        ga[i][4] = g1.x; ga[i][5] = g1.y; ga[i][6] = g1.z; ga[i][7] = g1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc_g[i][j] = acc_b[i][j] = 0.f;
+            if (HAS_B) acc_s[HAS_B ? i : 0][j] = 0.f;
+        }
+    }
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    for (int s = 0; s < stages; ++s)
+        fast_issue<NTENS>(ring + (size_t)s * NTENS * row_bytes, &bars[s], src, warp0 + (long long)s * nwarps, p.rows, row_bytes, lane);
+    const float inv_c = 1.0f / (float)C;
+    const float keep_b = DROP ? 1.0f / (1.0f - p.drop_b) : 1.0f;
+    unsigned char* DA = reinterpret_cast<unsigned char*>(p.da);
+    unsigned char* DB = reinterpret_cast<unsigned char*>(p.db);
+    int it = 0;
+    for (long long row = warp0; row < p.rows; row += nwarps, ++it) {
+        const int slot = it % stages;
+        const float mean = p.mean[row], rstd = p.rstd[row];
+        unsigned keep = 0xffffffffu;
+        if (HAS_B && DROP) keep = res_keep_bits<NV>(p.seed_b, row, C, off, p.drop_b);
+        mbar_wait(&bars[slot], (uint32_t)((it / stages) & 1));
+        const unsigned char* sm = ring + (size_t)slot * NTENS * row_bytes;
+        uint4 va[NV], vg[NV], vb[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            va[i] = *reinterpret_cast<const uint4*>(sm + off[i]);
+            vg[i] = *reinterpret_cast<const uint4*>(sm + row_bytes + off[i]);
+            if (HAS_B) vb[i] = *reinterpret_cast<const uint4*>(sm + 2 * row_bytes + off[i]);
+        }
+        __syncwarp();
+        fast_issue<NTENS>(ring + (size_t)slot * NTENS * row_bytes, &bars[slot], src, row + (long long)stages * nwarps, p.rows,
+                          row_bytes, lane);
+        float xh[NV][8], g[NV][8];
+        float s1 = 0.f, s2 = 0.f;
+        const float nmr = -mean * rstd;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            unpack8(va[i], xh[i]);
+            unpack8(vg[i], g[i]);
+            if (HAS_B) {
+                float t[8];
+                unpack8(vb[i], t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (DROP) t[j] = ((keep >> (8 * i + j)) & 1u) ? t[j] * keep_b : 0.f;
+                    xh[i][j] += t[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[i][j] = fmaf(xh[i][j], rstd, nmr);
+                acc_g[i][j] = fmaf(g[i][j], xh[i][j], acc_g[i][j]);
+                acc_b[i][j] += g[i][j];
+                g[i][j] *= ga[i][j];
+                s1 += g[i][j];
+                s2 = fmaf(g[i][j], xh[i][j], s2);
+            }
+        }
+        s1 = warp_sum(s1) * inv_c;
+        s2 = warp_sum(s2) * inv_c;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - s1 - xh[i][j] * s2);
+            if (DA != nullptr) *reinterpret_cast<uint4*>(DA + row * row_bytes + off[i]) = pack8(o);
+            if (HAS_B) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (DROP) o[j] = ((keep >> (8 * i + j)) & 1u) ? o[j] * keep_b : 0.f;
+                    acc_s[HAS_B ? i : 0][j] += o[j];
+                }
+                if (DB != nullptr) *reinterpret_cast<uint4*>(DB + row * row_bytes + off[i]) = pack8(o);
+            }
+        }
+    }
+    // CTA reduction of the column accumulators through shared memory (the rings are idle now), then one global
+    // atomic per channel and CTA
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(smem_raw);  // [dgamma | dbeta | dbias_b] x C
+    for (int c = threadIdx.x; c < 3 * C; c += blockDim.x) red[c] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (off[i] >> 1) + j;
+            atomicAdd(&red[c], acc_g[i][j]);
+            atomicAdd(&red[C + c], acc_b[i][j]);
+            if (HAS_B) atomicAdd(&red[2 * C + c], acc_s[HAS_B ? i : 0][j]);
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (p.dgamma != nullptr) atomicAdd(p.dgamma + c, red[c]);
+        if (p.dbeta != nullptr) atomicAdd(p.dbeta + c, red[C + c]);
+        if (HAS_B && dbias_b != nullptr) atomicAdd(dbias_b + c, red[2 * C + c]);
+    }
+}
+
+// dispatch of the residual-norm kernels; -1 when the generic path must be used
+static int launch_resln_fast(const RowLnParams& p, bool bwd, float* dbias_b, cudaStream_t st) {
+    if (p.act != 0 || p.gamma == nullptr || p.post != nullptr || p.drop_out > 0.f) return -1;
+    if (p.gw != p.gr || p.C % 256 || p.C < 512 || p.C > 1024) return -1;
+    if (p.b == nullptr && p.drop_b > 0.f) return -1;
+    if (bwd && (p.b != nullptr) != (p.db != nullptr || dbias_b != nullptr)) return -1;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(p.a) | reinterpret_cast<uintptr_t>(p.b) | reinterpret_cast<uintptr_t>(p.y) |
+                         reinterpret_cast<uintptr_t>(p.dy) | reinterpret_cast<uintptr_t>(p.da) | reinterpret_cast<uintptr_t>(p.db) |
+                         reinterpret_cast<uintptr_t>(p.gamma) | reinterpret_cast<uintptr_t>(p.beta);
+    if (al & 15) return -1;
+    const int nv = p.C / 256;
+    const bool has_b = p.b != nullptr, drop = p.drop_b > 0.f;
+    const int ntens = bwd ? (has_b ? 3 : 2) : (has_b ? 2 : 1);
+    const int row_bytes = p.C * 2;
+    const size_t fixed = (bwd ? 0 : (size_t)2 * p.C * sizeof(float)) + (size_t)ROWLN_WARPS * FAST_STAGES_MAX * 8;
+    const size_t per_stage = (size_t)ROWLN_WARPS * ntens * row_bytes;
+    const size_t budget = bwd ? 200 * 1024 : 110 * 1024;
+    int stages = (int)((budget - fixed) / per_stage);
+    if (stages > FAST_STAGES_MAX) stages = FAST_STAGES_MAX;
+    if (stages < 2) return -1;
+    size_t smem = per_stage * stages + fixed;
+    if (bwd && smem < (size_t)3 * p.C * sizeof(float)) smem = (size_t)3 * p.C * sizeof(float);
+    const long long blocks_needed = ceil_div64(p.rows, ROWLN_WARPS);
+    const long long cap = (long long)a2v_num_sms() * (bwd ? 1 : 2);
+    int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+    if (grid < 1) grid = 1;
+#define A2V_RES(KF, KB)                                                                                          \
+    do {                                                                                                         \
+        static size_t conf[2] = {0, 0};                                                                          \
+        if (smem > conf[bwd ? 1 : 0]) {                                                                          \
+            cudaError_t e = bwd ? cudaFuncSetAttribute(KB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) \
+                                : cudaFuncSetAttribute(KF, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) {                                                                              \
+                a2v_set_error("rowln(res): cudaFuncSetAttribute(%zu) failed", smem);                             \
+                return A2V_ERR_CUDA;                                                                             \
+            }                                                                                                    \
+            conf[bwd ? 1 : 0] = smem;                                                                            \
+        }                                                                                                        \
+        if (bwd) KB<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages, dbias_b);                                    \
+        else KF<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages);                                                 \
+    } while (0)
+#define A2V_RES_NV(N)                                                                                   \
+    do {                                                                                                \
+        if (has_b && drop) A2V_RES((resln_fwd_kernel<N, true, true>), (resln_bwd_kernel<N, true, true>)); \
+        else if (has_b) A2V_RES((resln_fwd_kernel<N, true, false>), (resln_bwd_kernel<N, true, false>));  \
+        else A2V_RES((resln_fwd_kernel<N, false, false>), (resln_bwd_kernel<N, false, false>));           \
+    } while (0)
+    switch (nv) {
+        case 2: A2V_RES_NV(2); break;
+        case 3: A2V_RES_NV(3); break;
+        default: A2V_RES_NV(4); break;
+    }
+#undef A2V_RES
+#undef A2V_RES_NV
+    return a2v_check_launch(bwd ? "rowln_bwd(res)" : "rowln_fwd(res)");
+}
+
 // dispatch test + launch of the specialised kernels; returns -1 when the generic path must be used
 static int launch_rowln_fast(const RowLnParams& p, bool bwd, cudaStream_t st) {
     if (p.act != 1 || p.gamma != nullptr || p.beta != nullptr || p.b != nullptr) return -1;
@@ -996,6 +1307,8 @@ extern "C" int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     if (d->dtype == A2V_BF16) {
         rc = launch_rowln_fast(p, false, st);
         if (rc >= 0) return rc;
+        rc = launch_resln_fast(p, false, nullptr, st);
+        if (rc >= 0) return rc;
         rc = launch_rowln128(p, false, st);
         if (rc >= 0) return rc;
     }
@@ -1008,14 +1321,19 @@ extern "C" int a2v_rowln_bwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     A2V_REQUIRE(d->dy != nullptr && d->mean != nullptr && d->rstd != nullptr,
                 "rowln_bwd: dy / saved mean / saved rstd are required");
     A2V_REQUIRE(d->db == nullptr || d->b != nullptr, "rowln_bwd: db requested without b");
+    A2V_REQUIRE(d->dbias_b == nullptr || d->db != nullptr, "rowln_bwd: dbias_b (column sums of db) requested without db");
     if (d->rows == 0) return A2V_OK;
     RowLnParams p = to_params(d);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (d->dtype == A2V_BF16) {
         rc = launch_rowln_fast(p, true, st);
         if (rc >= 0) return rc;
+        rc = launch_resln_fast(p, true, d->dbias_b, st);
+        if (rc >= 0) return rc;
         rc = launch_rowln128(p, true, st);
         if (rc >= 0) return rc;
     }
-    return d->dtype == A2V_F32 ? launch_rowln<float>(p, true, st) : launch_rowln<bf16>(p, true, st);
+    rc = d->dtype == A2V_F32 ? launch_rowln<float>(p, true, st) : launch_rowln<bf16>(p, true, st);
+    if (rc != A2V_OK || d->dbias_b == nullptr) return rc;
+    return a2v_colsum(d->dtype, d->db, d->dbias_b, d->rows, d->channels, stream);  // generic path: separate reduction
 }

@@ -147,6 +147,79 @@ __global__ void __launch_bounds__(256) relayout_kernel(const RelayoutParams p) {
     }
 }
 
+// Batched re-layout: one launch walks a DEVICE-resident table of re-layout items (blockIdx.y = item). The
+// weight packs of a model are rebuilt after every optimizer / EMA update (about 150 items per step at the
+// large config, most of them a few MB); one table-driven launch replaces as many dependent small launches.
+// 32-bit index arithmetic (every item is far below 2^31 elements; checked when the table is built).
+template <typename TI, typename TO>
+__device__ __forceinline__ void relayout_item_body(const a2v_relayout_item& it) {
+    const TI* in = reinterpret_cast<const TI*>(it.in);
+    TO* out = reinterpret_cast<TO*>(it.out);
+    const uint32_t d1 = (uint32_t)it.dims[1], d2 = (uint32_t)it.dims[2], d3 = (uint32_t)it.dims[3];
+    const uint32_t total = (uint32_t)(it.dims[0] * it.dims[1] * it.dims[2] * it.dims[3]);
+    const long long is0 = it.in_strides[0], is1 = it.in_strides[1], is2 = it.in_strides[2], is3 = it.in_strides[3];
+    const long long os0 = it.out_strides[0], os1 = it.out_strides[1], os2 = it.out_strides[2], os3 = it.out_strides[3];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t rem = i;
+        const uint32_t i3 = rem % d3; rem /= d3;
+        const uint32_t i2 = rem % d2; rem /= d2;
+        const uint32_t i1 = rem % d1; rem /= d1;
+        const long long src = it.in_offset + rem * is0 + i1 * is1 + i2 * is2 + i3 * is3;
+        const long long dst = it.out_offset + rem * os0 + i1 * os1 + i2 * os2 + i3 * os3;
+        float v = to_f32(in[src]);
+        if (it.accumulate) v += to_f32(out[dst]);
+        out[dst] = from_f32<TO>(v);
+        if (it.zero_src) const_cast<TI*>(in)[src] = from_f32<TI>(0.f);
+    }
+}
+
+// 2-D transposing items (dims (1, 1, K, N), input contiguous along K, output contiguous along N: the W -> W^T packs
+// of every Linear): 32x32 tiles through shared memory so that both the reads and the writes are coalesced.
+template <typename TI, typename TO>
+__device__ __forceinline__ void relayout_item_transpose(const a2v_relayout_item& it, float (*tile)[33]) {
+    const TI* in = reinterpret_cast<const TI*>(it.in) + it.in_offset;
+    TO* out = reinterpret_cast<TO*>(it.out) + it.out_offset;
+    const int K = (int)it.dims[2], N = (int)it.dims[3];
+    const long long is3 = it.in_strides[3], os2 = it.out_strides[2];
+    const int tk = (K + 31) / 32, tn = (N + 31) / 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
+        const int k0 = (t % tk) * 32, n0 = (t / tk) * 32;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = n0 + ty + 8 * r, k = k0 + tx;
+            tile[ty + 8 * r][tx] = (n < N && k < K) ? to_f32(in[n * is3 + k]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int k = k0 + ty + 8 * r, n = n0 + tx;
+            if (k < K && n < N) {
+                float v = tile[tx][ty + 8 * r];
+                if (it.accumulate) v += to_f32(out[k * os2 + n]);
+                out[k * os2 + n] = from_f32<TO>(v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) relayout_batch_kernel(const a2v_relayout_item* __restrict__ items) {
+    __shared__ a2v_relayout_item it;
+    __shared__ float tile[32][33];
+    if (threadIdx.x == 0) it = items[blockIdx.y];
+    __syncthreads();
+    if (it.dims[0] == 1 && it.dims[1] == 1 && it.in_strides[2] == 1 && it.out_strides[3] == 1 && !it.zero_src &&
+        it.dims[2] >= 32 && it.dims[3] >= 32) {
+        if (it.in_dtype == A2V_F32 && it.out_dtype == A2V_BF16) { relayout_item_transpose<float, bf16>(it, tile); return; }
+        if (it.in_dtype == A2V_F32 && it.out_dtype == A2V_F32) { relayout_item_transpose<float, float>(it, tile); return; }
+    }
+    if (it.in_dtype == A2V_F32 && it.out_dtype == A2V_BF16) relayout_item_body<float, bf16>(it);
+    else if (it.in_dtype == A2V_F32 && it.out_dtype == A2V_F32) relayout_item_body<float, float>(it);
+    else if (it.in_dtype == A2V_BF16 && it.out_dtype == A2V_BF16) relayout_item_body<bf16, bf16>(it);
+    else if (it.in_dtype == A2V_BF16 && it.out_dtype == A2V_F32) relayout_item_body<bf16, float>(it);
+}
+
 // ---------------------------------------------------------------- flat elementwise
 // out = dh * GELU'(u): backward of timm Mlp's activation (modules.py:312-317), applied to the output of
 // the fc2 data-gradient GEMM (kept out of that GEMM's epilogue: a latency-bound read there costs 5x more).
@@ -164,6 +237,36 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const T* __restrict__ dh
         store4(out + 8 * i, *reinterpret_cast<float(*)[4]>(a));
         store4(out + 8 * i + 4, *reinterpret_cast<float(*)[4]>(a + 4));
     }
+}
+
+// The same with the column sums of the result fused in (the bias gradient of fc1, rows x C with C % 8 == 0): the
+// launch uses a thread count that is a multiple of C / 8, so a thread keeps ONE group of 8 columns over its
+// whole grid-stride loop and accumulates their sums in registers; one 16-byte vector reduction pair per thread at
+// the end. Saves a separate pass over the (rows x 4 D) tensor.
+template <typename T>
+__global__ void __launch_bounds__(256) dgelu_mul_colsum_kernel(const T* __restrict__ dh, const T* __restrict__ u,
+                                                               T* __restrict__ out, long long n8, int cols8,
+                                                               float* __restrict__ colsum) {
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long i = t0; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        load4(dh + 8 * i, *reinterpret_cast<float(*)[4]>(a));
+        load4(dh + 8 * i + 4, *reinterpret_cast<float(*)[4]>(a + 4));
+        load4(u + 8 * i, *reinterpret_cast<float(*)[4]>(b));
+        load4(u + 8 * i + 4, *reinterpret_cast<float(*)[4]>(b + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] *= gelu_grad_t<T>(b[j]);
+            a[j] = to_f32(from_f32<T>(a[j]));  // sum what is stored
+            acc[j] += a[j];
+        }
+        store4(out + 8 * i, *reinterpret_cast<float(*)[4]>(a));
+        store4(out + 8 * i + 4, *reinterpret_cast<float(*)[4]>(a + 4));
+    }
+    float* dst = colsum + (t0 % cols8) * 8;
+    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(acc[0], acc[1], acc[2], acc[3]));
+    atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
 }
 
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
@@ -358,6 +461,16 @@ extern "C" int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, voi
     return a2v_check_launch("cast_strided");
 }
 
+extern "C" int a2v_relayout_batch(const a2v_relayout_item* items_device, int n_items, int blocks_per_item,
+                                  a2v_stream_t stream) {
+    A2V_REQUIRE(items_device != nullptr && n_items >= 0 && n_items <= 65535, "relayout_batch: bad table (n=%d)", n_items);
+    A2V_REQUIRE(blocks_per_item >= 1 && blocks_per_item <= 4096, "relayout_batch: blocks_per_item out of range");
+    if (n_items == 0) return A2V_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    relayout_batch_kernel<<<dim3(blocks_per_item, n_items), 256, 0, st>>>(items_device);
+    return a2v_check_launch("relayout_batch");
+}
+
 extern "C" int a2v_relayout(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
                             const int64_t* in_strides4, int64_t in_offset, const int64_t* out_strides4,
                             int64_t out_offset, int accumulate, a2v_stream_t stream) {
@@ -404,6 +517,32 @@ extern "C" int a2v_dgelu_mul(int dtype, const void* dh, const void* u, void* out
     else
         dgelu_mul_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dh, (const bf16*)u, (bf16*)out, n / 8);
     return a2v_check_launch("dgelu_mul");
+}
+
+extern "C" int a2v_dgelu_mul_colsum(int dtype, const void* dh, const void* u, void* out, int64_t rows, int C,
+                                    float* colsum, a2v_stream_t stream) {
+    A2V_REQUIRE(dtype == A2V_F32 || dtype == A2V_BF16, "dgelu_mul_colsum: bad dtype");
+    A2V_REQUIRE(dh && u && out && colsum && rows >= 0 && C > 0 && C % 8 == 0, "dgelu_mul_colsum: C must be a multiple of 8");
+    A2V_REQUIRE((reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "dgelu_mul_colsum: colsum must be 16-byte aligned");
+    if (rows == 0) return A2V_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // thread count = multiple of C / 8: grid = k * (cols8 / gcd(cols8, 256))
+    const int cols8 = C / 8;
+    int g = cols8, h = 256;
+    while (h) { const int r = g % h; g = h; h = r; }
+    const int unit = cols8 / g;
+    const long long want = (long long)a2v_num_sms() * 8;
+    const long long need = ceil_div64(rows * cols8, 256);
+    long long grid = (want < need ? want : need) / unit * unit;
+    if (grid < unit) grid = unit;
+    A2V_REQUIRE(grid <= 65535 * 16, "dgelu_mul_colsum: unsupported column count %d", C);
+    if (dtype == A2V_F32)
+        dgelu_mul_colsum_kernel<float><<<(int)grid, 256, 0, st>>>((const float*)dh, (const float*)u, (float*)out,
+                                                                 rows * cols8, cols8, colsum);
+    else
+        dgelu_mul_colsum_kernel<bf16><<<(int)grid, 256, 0, st>>>((const bf16*)dh, (const bf16*)u, (bf16*)out,
+                                                                rows * cols8, cols8, colsum);
+    return a2v_check_launch("dgelu_mul_colsum");
 }
 
 extern "C" int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream) {

@@ -125,6 +125,7 @@ class PretrainEngine:
             self.hann = torch.hann_window(n_fft).float().to(self.device)
             self.aweight = torch.from_numpy(a_weight_table(cfg.sample_rate, n_fft)).float().to(self.device)
 
+        self._pack_table_s = self._pack_table_t = self._unpack_table = None
         self._build_packs()
         self.ctx = None
         self.kernel_launches = 0
@@ -280,9 +281,17 @@ class PretrainEngine:
             else:
                 W.fwd[n] = S.view(n, self.S16)
             W.split[n] = S.shapes[n][1]
+        if not self.fp32 and self._pack_table_s is not None:
+            # every operand buffer is persistent: one table-driven launch rebuilds all the packs
+            self._pack_table_s.run()
+            self._student_dirty = False
+            return
+        table = None if self.fp32 else ops.RelayoutTable(self.device)
         for key, pk in self.sp.items():
             name, kind = key.split("|")
             buf = P.materialize(pk, S.view(name), self.fp32)
+            if table is not None:
+                table.add(S.view(name), buf, pk.dims, pk.in_strides, pk.in_off, pk.out_strides, 0)
             if kind == "F":
                 W.fwd[name], W.split[name] = buf, pk.split_k
             elif kind == "T":
@@ -293,6 +302,7 @@ class PretrainEngine:
             if n not in W.f32:
                 W.f32[n] = S.view(n)
         W.alibi = self._alibi_of(S, self.WS)
+        self._pack_table_s = table
         self._student_dirty = False
 
     def _alibi_of(self, F: P.FlatParams, W: _Weights) -> torch.Tensor:
@@ -316,12 +326,20 @@ class PretrainEngine:
             else:
                 W.fwd[n] = E.view(n, self.T16)
             W.split[n] = E.shapes[n][1]
+        if not self.fp32 and self._pack_table_t is not None:
+            self._pack_table_t.run()
+            self._teacher_dirty = False
+            return
+        table = None if self.fp32 else ops.RelayoutTable(self.device)
         for key, pk in self.tp.items():
             name, _ = key.split("|")
             W.fwd[name], W.split[name] = P.materialize(pk, E.view(name), self.fp32), pk.split_k
+            if table is not None:
+                table.add(E.view(name), W.fwd[name], pk.dims, pk.in_strides, pk.in_off, pk.out_strides, 0)
         for n in E.names:
             W.f32[n] = E.view(n)
         W.alibi = self._alibi_of(E, W)
+        self._pack_table_t = table
         self._teacher_dirty = False
 
     # ------------------------------------------------------------------------------------ GEMM helpers
@@ -613,18 +631,15 @@ class PretrainEngine:
         pre, G, f = s.pre, self.G, W.f32
         dz2, dt = ops.rowln_bwd(s.c2, dx2, s.x1, s.t, f[pre + "norm2.weight"], f[pre + "norm2.bias"], None, None,
                                 s.m2, s.r2, seed_b=s.s2, training=train, dgamma=G(pre + "norm2.weight"),
-                                dbeta=G(pre + "norm2.bias"))
-        ops.colsum(dt, G(pre + "mlp.fc2.bias"))
+                                dbeta=G(pre + "norm2.bias"), dbias_b=G(pre + "mlp.fc2.bias"))
         self.wgrad(dt, s.h, G(pre + "mlp.fc2.weight"))
-        du = ops.dgelu_mul(self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True), s.u)
-        ops.colsum(du, G(pre + "mlp.fc1.bias"))
+        du = ops.dgelu_mul(self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True), s.u, colsum=G(pre + "mlp.fc1.bias"))
         self.wgrad(du, s.x1, G(pre + "mlp.fc1.weight"))
         dx1 = self.lin(du, W, pre + "mlp.fc1.weight", dgrad=True, residual=dz2)
         del du, dz2, dt
         dz1, dpr = ops.rowln_bwd(s.c1, dx1, s.x, s.pr, f[pre + "norm1.weight"], f[pre + "norm1.bias"], None, None,
                                  s.m1, s.r1, seed_b=s.s1, training=train, dgamma=G(pre + "norm1.weight"),
-                                 dbeta=G(pre + "norm1.bias"))
-        ops.colsum(dpr, G(pre + "attn.proj.bias"))
+                                 dbeta=G(pre + "norm1.bias"), dbias_b=G(pre + "attn.proj.bias"))
         self.wgrad(dpr, s.ao.view(rows * seq, self.D), G(pre + "attn.proj.weight"))
         dao = self.lin(dpr, W, pre + "attn.proj.weight", dgrad=True)
         dal = G(ENC + "alibi_scale").view(-1) if self.a.learned_alibi_scale else None
@@ -749,6 +764,17 @@ class PretrainEngine:
 
     def _unpack_grads(self) -> None:
         """Packed-layout weight gradients -> checkpoint-layout views of the flat gradient buffer."""
+        if not self.fp32:
+            if self._unpack_table is None:
+                t = self._unpack_table = ops.RelayoutTable(self.device)
+                for key, buf in self.gpacked.items():
+                    name, _ = key.split("|")
+                    pk = self.sp[key]
+                    strides = pk.gt_strides if key in self.gt_keys else pk.out_strides
+                    # G += packed, and the packed accumulator is cleared for the next backward in the same pass
+                    t.add(buf, self.G(name), pk.dims, strides, 0, pk.in_strides, pk.in_off, accumulate=True, zero_src=True)
+            self._unpack_table.run()
+            return
         for key, buf in self.gpacked.items():
             name, _ = key.split("|")
             P.unpack_grad(self.sp[key], buf, self.G(name), transposed=key in self.gt_keys)  # G += packed

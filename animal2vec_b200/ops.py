@@ -5,7 +5,7 @@ these functions only allocate outputs with torch and pass raw pointers + the cur
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Sequence
+from typing import Optional, Sequence, List
 
 import torch
 
@@ -42,6 +42,7 @@ class RowLnDesc(C.Structure):
         ("dbeta", C.c_void_p),
         ("dact_alpha", C.c_void_p),
         ("dact_beta", C.c_void_p),
+        ("dbias_b", C.c_void_p),
     ]
 
 
@@ -165,14 +166,16 @@ def rowln_fwd(cfg: RowLnCfg, a, b=None, gamma=None, beta=None, act_alpha=None, a
 
 
 def rowln_bwd(cfg: RowLnCfg, dy, a, b, gamma, beta, act_alpha, act_beta, mean, rstd, *, seed_b=0, seed_out=0,
-              training=True, want_db=True, dgamma=None, dbeta=None, dact_alpha=None, dact_beta=None):
-    """Returns (da, db). Parameter gradients are accumulated into the given fp32 buffers."""
+              training=True, want_db=True, dgamma=None, dbeta=None, dact_alpha=None, dact_beta=None, dbias_b=None):
+    """Returns (da, db). Parameter gradients are accumulated into the given fp32 buffers; ``dbias_b`` (optional)
+    accumulates the column sums of db, i.e. the bias gradient of the Linear whose output was ``b``."""
     assert dy.is_contiguous() and dy.dtype == a.dtype
     da = torch.empty_like(a)
     db = torch.empty_like(a) if (b is not None and want_db) else None
     d = _rowln_desc(cfg, a, b, gamma, beta, act_alpha, act_beta, None, None, mean, rstd, seed_b, seed_out, training)
     d.dy, d.da, d.db = _p(dy), _p(da), _p(db)
     d.dgamma, d.dbeta, d.dact_alpha, d.dact_beta = _p(dgamma), _p(dbeta), _p(dact_alpha), _p(dact_beta)
+    d.dbias_b = _p(dbias_b)
     _call("a2v_rowln_bwd", a, C.byref(d))
     return da, db
 
@@ -303,10 +306,18 @@ def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def dgelu_mul(dh: torch.Tensor, u: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = dh * GELU'(u) (in place on ``dh`` when ``out`` is None)."""
+def dgelu_mul(dh: torch.Tensor, u: torch.Tensor, out: Optional[torch.Tensor] = None,
+              colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = dh * GELU'(u) (in place on ``dh`` when ``out`` is None); ``colsum`` (fp32, one per column of the
+    last dimension) optionally accumulates the column sums of the result in the same pass."""
     assert dh.is_contiguous() and u.is_contiguous() and dh.shape == u.shape and dh.dtype == u.dtype
     out = dh if out is None else out
+    if colsum is not None:
+        c = dh.shape[-1]
+        assert colsum.dtype == torch.float32 and colsum.numel() == c
+        _call("a2v_dgelu_mul_colsum", dh, L.dtype_code(dh), _p(dh), _p(u), _p(out), C.c_int64(dh.numel() // c), c,
+              _p(colsum))
+        return out
     _call("a2v_dgelu_mul", dh, L.dtype_code(dh), _p(dh), _p(u), _p(out), C.c_int64(dh.numel()))
     return out
 
@@ -339,6 +350,65 @@ def relayout(src: torch.Tensor, dst: torch.Tensor, dims, in_strides, in_off, out
     _call("a2v_relayout", src, L.dtype_code(src), L.dtype_code(dst), _p(src), _p(dst), dd, si, C.c_int64(in_off), so,
           C.c_int64(out_off), int(accumulate))
     return dst
+
+
+class RelayoutItem(C.Structure):
+    _fields_ = [
+        ("in_", C.c_void_p),
+        ("out", C.c_void_p),
+        ("dims", C.c_int64 * 4),
+        ("in_strides", C.c_int64 * 4),
+        ("out_strides", C.c_int64 * 4),
+        ("in_offset", C.c_int64),
+        ("out_offset", C.c_int64),
+        ("in_dtype", C.c_int32),
+        ("out_dtype", C.c_int32),
+        ("accumulate", C.c_int32),
+        ("zero_src", C.c_int32),
+    ]
+
+
+class RelayoutTable:
+    """A device-resident table of re-layout items (see a2v_relayout_batch): built once for a fixed set of
+    persistent source / destination buffers, replayed with one launch. Keeps the tensors alive."""
+
+    def __init__(self, device):
+        self.device = device
+        self.items: List[RelayoutItem] = []
+        self.keep: list = []
+        self.table: Optional[torch.Tensor] = None
+
+    def add(self, src: torch.Tensor, dst: torch.Tensor, dims, in_strides, in_off, out_strides, out_off,
+            accumulate: bool = False, zero_src: bool = False) -> None:
+        dims, in_strides, out_strides = list(dims), list(in_strides), list(out_strides)
+        while len(dims) < 4:
+            dims.insert(0, 1)
+            in_strides.insert(0, 0)
+            out_strides.insert(0, 0)
+        total = 1
+        for v in dims:
+            assert v > 0
+            total *= v
+        assert total < 2 ** 31, "relayout item too large for the batched kernel"
+        it = RelayoutItem()
+        it.in_, it.out = src.data_ptr(), dst.data_ptr()
+        it.dims = (C.c_int64 * 4)(*dims)
+        it.in_strides = (C.c_int64 * 4)(*in_strides)
+        it.out_strides = (C.c_int64 * 4)(*out_strides)
+        it.in_offset, it.out_offset = in_off, out_off
+        it.in_dtype, it.out_dtype = L.dtype_code(src), L.dtype_code(dst)
+        it.accumulate, it.zero_src = int(accumulate), int(zero_src)
+        self.items.append(it)
+        self.keep += [src, dst]
+        self.table = None
+
+    def run(self, blocks_per_item: int = 48) -> None:
+        if not self.items:
+            return
+        if self.table is None:
+            raw = b"".join(bytes(it) for it in self.items)
+            self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        _call("a2v_relayout_batch", self.table, _p(self.table), len(self.items), blocks_per_item)
 
 
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

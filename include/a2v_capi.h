@@ -176,6 +176,7 @@ typedef struct {
     float* dbeta;
     float* dact_alpha;
     float* dact_beta;
+    float* dbias_b;            /* optional: += column sums of db (the bias gradient of the Linear that produced b) */
 } a2v_rowln_desc;
 
 int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream);
@@ -240,6 +241,9 @@ int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t*
 int a2v_colsum(int dtype, const void* x, float* out, int64_t rows, int C, a2v_stream_t stream);
 /* out = dh * GELU'(u) elementwise (backward of timm Mlp's GELU, nn/modalities/modules.py:312-317). */
 int a2v_dgelu_mul(int dtype, const void* dh, const void* u, void* out, int64_t n, a2v_stream_t stream);
+/* The same over a (rows x C) tensor with colsum[c] += sum over rows of out[:, c] fused in (fc1.bias gradient). */
+int a2v_dgelu_mul_colsum(int dtype, const void* dh, const void* u, void* out, int64_t rows, int C, float* colsum,
+                         a2v_stream_t stream);
 int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
                      const int64_t* in_strides4, int64_t in_offset, a2v_stream_t stream);
 /* general 4-D re-layout with cast: out[out_offset + i.out_strides] (+)= in[in_offset + i.in_strides]
@@ -249,6 +253,21 @@ int a2v_cast_strided(int in_dtype, int out_dtype, const void* in, void* out, con
 int a2v_relayout(int in_dtype, int out_dtype, const void* in, void* out, const int64_t* dims4,
                  const int64_t* in_strides4, int64_t in_offset, const int64_t* out_strides4, int64_t out_offset,
                  int accumulate, a2v_stream_t stream);
+/* Batched form: one launch over a DEVICE-resident table of items (same semantics per item; ``zero_src`` also
+ * clears every source element after it was read, which is how the packed weight-gradient buffers are emptied
+ * when they are folded into the checkpoint-layout gradient). Items must not alias each other's outputs and
+ * each item must have fewer than 2^31 elements. The caller owns the table. */
+typedef struct {
+    const void* in;
+    void* out;
+    int64_t dims[4];
+    int64_t in_strides[4];
+    int64_t out_strides[4];
+    int64_t in_offset, out_offset;
+    int32_t in_dtype, out_dtype;
+    int32_t accumulate, zero_src;
+} a2v_relayout_item;
+int a2v_relayout_batch(const a2v_relayout_item* items_device, int n_items, int blocks_per_item, a2v_stream_t stream);
 int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream);
 int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream);
 int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_t n, float decay,

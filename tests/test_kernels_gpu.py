@@ -27,7 +27,9 @@ def _pswish(n, al, be):
     "rows,c,gw,gr,act,affine,two,post",
     [(37, 128, 128, 127, 2, True, False, False), (1000, 512, 512, 512, 1, True, False, False),
      (513, 1024, 1024, 1024, 0, True, True, False), (200, 1024, 64, 48, 1, False, False, True),
-     (64, 768, 768, 768, 1, False, False, False), (33, 64, 64, 64, 0, True, True, False)],
+     (64, 768, 768, 768, 1, False, False, False), (33, 64, 64, 64, 0, True, True, False),
+     (2500, 768, 768, 768, 0, True, True, False), (1301, 512, 512, 512, 0, True, False, False),
+     (3000, 1024, 1024, 1024, 0, True, False, False)],
 )
 def test_rowln(dtype, rows, c, gw, gr, act, affine, two, post):
     from animal2vec_b200 import ops
@@ -106,6 +108,33 @@ def test_rowln_dropout_consistency():
     assert torch.allclose(y2[k2], ref[k2] / 0.75, rtol=1e-4, atol=1e-5)
     y3, _, _ = ops.rowln_fwd(cfg2, x, seed_out=99, training=False)
     assert _rel(y3, ref) < 1e-5
+
+
+@pytest.mark.parametrize("c", [512, 768, 1024])
+def test_rowln_residual_bf16_dropout_matches_generic_path(c):
+    """The specialised bf16 residual-norm kernels (LN(a + drop(b)) * gamma + beta, fused bias-gradient column
+    sums) against the generic fp32 kernels with the SAME dropout seed (identical keep masks by construction)."""
+    from animal2vec_b200 import ops
+
+    rows = 2999
+    a = torch.randn(rows, c, device="cuda", generator=_g(1)).bfloat16()
+    b = torch.randn(rows, c, device="cuda", generator=_g(2)).bfloat16()
+    dy = torch.randn(rows, c, device="cuda", generator=_g(3)).bfloat16()
+    gamma = torch.randn(c, device="cuda", generator=_g(4))
+    beta = torch.randn(c, device="cuda", generator=_g(5))
+    cfg = ops.RowLnCfg(c, 1e-5, drop_b=0.1)
+    res = {}
+    for name, cast in (("bf16", lambda t: t), ("fp32", lambda t: t.float())):
+        y, m, r = ops.rowln_fwd(cfg, cast(a), cast(b), gamma, beta, seed_b=77)
+        dg, dbt, dbias = (torch.zeros(c, device="cuda") for _ in range(3))
+        da, db = ops.rowln_bwd(cfg, cast(dy), cast(a), cast(b), gamma, beta, None, None, m, r, seed_b=77, dgamma=dg,
+                               dbeta=dbt, dbias_b=dbias)
+        res[name] = (y.float(), da.float(), db.float(), dg, dbt, dbias, m, r)
+    for i, tol in enumerate((8e-3, 8e-3, 8e-3, 8e-3, 8e-3, 2e-2, 1e-4, 1e-4)):
+        assert _rel(res["bf16"][i], res["fp32"][i]) < tol, i
+    assert torch.equal(res["bf16"][2] != 0, res["fp32"][2] != 0)  # identical dropout masks
+    assert _rel(res["bf16"][5], res["bf16"][2].sum(0)) < 1e-2      # fused column sums = sums of the stored db
+    assert abs((res["bf16"][2] != 0).float().mean().item() - 0.9) < 0.01
 
 
 # --------------------------------------------------------------------------------------- attention
@@ -417,3 +446,60 @@ def test_mixup():
     p_ref = (1 / (1 + 10 ** ((G1 - G2) / 20) * (1 - r) / r)).unsqueeze(-1)
     ref = (p_ref * x + (1 - p_ref) * x[perm.long()]) / torch.sqrt(p_ref ** 2 + (1 - p_ref) ** 2)
     assert _rel(out, ref) < 1e-4
+
+
+# --------------------------------------------------------------------------------------- batched re-layout, fused dgelu
+def test_relayout_batch_matches_single_launches():
+    """One table-driven launch == the per-item launches: Linear transposes (tiled path), tap-major conv packs
+    (generic path, padded), and gradient unpacking with accumulate + source clearing."""
+    from animal2vec_b200 import ops, params as P
+
+    dev = "cuda"
+    packs = [P.pack_linear_t("a", 96, 160), P.pack_linear_t("b", 1024, 512), P.pack_conv_fwd("c", 4, 48, 64, 7, ngp=64, cgp=64),
+             P.pack_conv_dgrad("d", 4, 64, 64, 19), P.pack_cols_padded_t("e", 128, 4, 48, 64), P.pack_bias_padded("f", 4, 48, 64)]
+    srcs, ref, table, outs = [], [], ops.RelayoutTable(dev), []
+    for i, pk in enumerate(packs):
+        n_src = sum(max(0, (d_ - 1) * s_) for d_, s_ in zip(pk.dims, pk.in_strides)) + 1 + pk.in_off
+        src = torch.randn(n_src, device=dev, generator=_g(10 + i))
+        dt = torch.float32 if pk.is_bias else torch.bfloat16
+        a = torch.zeros(pk.out_shape, device=dev, dtype=dt)
+        b = torch.zeros(pk.out_shape, device=dev, dtype=dt)
+        ops.relayout(src, a, pk.dims, pk.in_strides, pk.in_off, pk.out_strides, 0)
+        table.add(src, b, pk.dims, pk.in_strides, pk.in_off, pk.out_strides, 0)
+        srcs.append(src); ref.append(a); outs.append(b)
+    table.run()
+    for a, b in zip(ref, outs):
+        assert torch.equal(a, b)
+    # inverse direction: G += packed (fp32), packed cleared
+    pk = packs[2]
+    packed = torch.randn(pk.gt_shape, device=dev, generator=_g(30))
+    g0 = torch.randn(4 * 48 * 64 * 7, device=dev, generator=_g(31))
+    want = g0.clone()
+    ops.relayout(packed, want, pk.dims, pk.gt_strides, 0, pk.in_strides, pk.in_off, accumulate=True)
+    got = g0.clone()
+    t2 = ops.RelayoutTable(dev)
+    p2 = packed.clone()
+    t2.add(p2, got, pk.dims, pk.gt_strides, 0, pk.in_strides, pk.in_off, accumulate=True, zero_src=True)
+    t2.run()
+    assert torch.equal(want, got)
+    # every REAL source element was cleared
+    probe = torch.zeros_like(want)
+    ops.relayout(p2, probe, pk.dims, pk.gt_strides, 0, pk.in_strides, pk.in_off)
+    assert probe.abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dgelu_mul_fused_colsum(dtype):
+    from animal2vec_b200 import ops
+
+    rows, c = 3001, 4096
+    dh = torch.randn(rows, c, device="cuda", generator=_g(1)).to(dtype)
+    u = torch.randn(rows, c, device="cuda", generator=_g(2)).to(dtype)
+    ur = u.float().clone().requires_grad_(True)
+    F.gelu(ur).backward(dh.float())
+    want = ops.dgelu_mul(dh.clone(), u)
+    cs = torch.zeros(c, device="cuda")
+    got = ops.dgelu_mul(dh.clone(), u, colsum=cs)
+    assert torch.equal(want, got)
+    assert _rel(got.float(), ur.grad) < (1e-5 if dtype == torch.float32 else 8e-3)
+    assert _rel(cs, got.float().sum(0)) < 1e-5
