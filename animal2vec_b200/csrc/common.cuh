@@ -117,6 +117,21 @@ __device__ __forceinline__ float gelu_erfc_grad(float x) {
     return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
+// 6-instruction GELU for the GEMM epilogues that write bf16 (tanh form, one MUFU): |error| vs the erf form
+// <= 5e-4 absolute, a tenth of the bf16 rounding of the stored value (relative L2 error of the bf16 result against
+// exact GELU: 1.67e-3 vs 1.65e-3 for the erf form). The saved pre-activation keeps the backward on the erf derivative.
+__device__ __forceinline__ float tanh_approx_f(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    const float x2 = x * x;
+    const float u = x * fmaf(0.0356774081f, x2, 0.7978845608f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, tanh_approx_f(u), hx);
+}
+
 __device__ __forceinline__ float gelu_fast(float x) { return gelu_erfc(x); }
 __device__ __forceinline__ float gelu_fast_grad(float x) { return gelu_erfc_grad(x); }
 template <typename T> __device__ __forceinline__ float gelu_t(float x);

@@ -416,7 +416,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     bf16* dst = reinterpret_cast<bf16*>(pass == 0 ? p.preact : p.c);
                     if (pass == 1) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = gelu_t<bf16>(x[i]);
+                        for (int i = 0; i < 32; ++i) x[i] = gelu_tanh_fast(x[i]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {

@@ -174,16 +174,37 @@ __global__ void __launch_bounds__(256) sinc_conv_wgrad_kernel(const float* __res
             sx[i] = (j < N + half) ? xb[reflect_index(j, N)] : 0.f;
         }
         __syncthreads();
-        for (int tl = 0; tl < SINC_TT; ++tl) {
-            const float4 d = *reinterpret_cast<const float4*>(sdy + tl * SINC_CPAD + lane * 4);
+        if (kpw <= 8) {
+            // sliding window: the 8 taps of time step tl + 1 reuse 7 of the 8 samples of step tl, so eight time steps
+            // cost 15 sample loads + 8 gradient loads for 256 FMAs (taps beyond K accumulate into unused slots)
+            for (int tl = 0; tl < SINC_TT; tl += 8) {
+                float xw[15];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-                if (k < kpw && k_begin + k < K) {
-                    const float xv = sx[tl + k_begin + k];
-                    acc[k][0] += d.x * xv;
-                    acc[k][1] += d.y * xv;
-                    acc[k][2] += d.z * xv;
-                    acc[k][3] += d.w * xv;
+                for (int i = 0; i < 15; ++i) xw[i] = sx[min(tl + k_begin + i, SINC_TT + K - 1)];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 d = *reinterpret_cast<const float4*>(sdy + (tl + u) * SINC_CPAD + lane * 4);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        acc[k][0] = fmaf(d.x, xw[u + k], acc[k][0]);
+                        acc[k][1] = fmaf(d.y, xw[u + k], acc[k][1]);
+                        acc[k][2] = fmaf(d.z, xw[u + k], acc[k][2]);
+                        acc[k][3] = fmaf(d.w, xw[u + k], acc[k][3]);
+                    }
+                }
+            }
+        } else {
+            for (int tl = 0; tl < SINC_TT; ++tl) {
+                const float4 d = *reinterpret_cast<const float4*>(sdy + tl * SINC_CPAD + lane * 4);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < kpw && k_begin + k < K) {
+                        const float xv = sx[tl + k_begin + k];
+                        acc[k][0] += d.x * xv;
+                        acc[k][1] += d.y * xv;
+                        acc[k][2] += d.z * xv;
+                        acc[k][3] += d.w * xv;
+                    }
                 }
             }
         }

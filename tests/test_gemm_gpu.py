@@ -52,6 +52,20 @@ def test_gemm_nt_epilogues():
     uu = u.clone().requires_grad_(True)
     F.gelu(uu).sum().backward()
     assert _rel(out2, (a.float() @ w.float().t()) * uu.grad) < 1e-5
+    # the compile-time bf16 epilogues (8-warp GELU variants with the staged bias vector; bias-only; residual)
+    for (mm, nn, kk) in ((515, 320, 256), (1000, 4096, 1024)):
+        a2, w2 = _randn(mm, kk, seed=5), _randn(nn, kk, scale=0.05, seed=6)
+        b2 = torch.randn(nn, device="cuda")
+        r2 = torch.randn(mm, nn, device="cuda").bfloat16()
+        u2 = a2.float() @ w2.float().t() + b2
+        pre16 = torch.empty(mm, nn, device="cuda", dtype=torch.bfloat16)
+        o1 = gemm.gemm_nt(a2, w2, out_dtype=torch.bfloat16, bias=b2, act=1, preact=pre16)
+        assert _rel(pre16, u2) < 4e-3 and _rel(o1, F.gelu(u2)) < 5e-3
+        o2 = gemm.gemm_nt(a2, w2, out_dtype=torch.bfloat16, bias=b2, act=1)
+        assert torch.equal(o1, o2)
+        assert (o1.float() - F.gelu(u2)).abs().max().item() < 2e-3 + 8e-3 * F.gelu(u2).abs().max().item()
+        assert _rel(gemm.gemm_nt(a2, w2, out_dtype=torch.bfloat16, bias=b2), u2) < 4e-3
+        assert _rel(gemm.gemm_nt(a2, w2, out_dtype=torch.bfloat16, residual=r2), u2 - b2 + r2.float()) < 4e-3
     # accumulate
     acc = torch.ones(m, n, device="cuda")
     gemm.gemm_nt(a, w, out=acc, accumulate=True)
