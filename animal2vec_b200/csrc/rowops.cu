@@ -439,8 +439,8 @@ __global__ void __launch_bounds__(256) rowln_bwd_kernel(const RowLnParams p, con
 // rows (16 groups x 48 real of 64 stored channels, optional residual). Compared with the generic kernels
 // above everything is resolved at compile time (no run-time feature tests inside the unrolled loops, a
 // fifth of the SASS, under 128 registers so two CTAs share an SM), every lane owns 16-byte chunks of
-// REAL channels only (pad chunks cost no arithmetic) and GELU costs 14
-// instructions (erfc form: y = relu(x) - |x| * erfc(|x|/sqrt2)/2).
+// REAL channels only (pad chunks cost no arithmetic) and GELU costs 6 instructions (tanh form with one MUFU
+// tanh.approx; both kernels are issue-bound, not HBM-bound, with the 14-instruction erfc form).
 // ---------------------------------------------------------------------------------------------
 struct ChunkMap {
     int cs, cr, ngroups;  // stored / real 16-byte chunks per channel group, groups per row
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256, 2) rowln_gelu_fwd_kernel(const RowLnParam
             if (HAS_POST) unpack8(vp[i], po);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                o[j] = gelu_erfc(z[i][j] * rstd);
+                o[j] = gelu_tanh_fast(z[i][j] * rstd);
                 if (HAS_POST) o[j] += po[j];
             }
             *reinterpret_cast<uint4*>(yrow + off[i]) = pack8(o);
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(256, 2) rowln_gelu_bwd_kernel(const RowLnParam
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 xh[i][j] = fmaf(xh[i][j], rstd, nmr);
-                g[i][j] *= gelu_erfc_grad(xh[i][j]);
+                g[i][j] *= gelu_tanh_fast_grad(xh[i][j]);
                 s1 += g[i][j];
                 s2 = fmaf(g[i][j], xh[i][j], s2);
             }
