@@ -40,6 +40,7 @@ struct AttnParams {
     const void* dout;
     void* dqkv;
     float* dalibi_scale;
+    const float* qk_bound;  // optional, (batch * H): max |q| * max |k| of the head (see attn_qk_bound_kernel)
 };
 
 __device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
@@ -86,6 +87,10 @@ constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 512;
 // of a kernel without static shared memory starts 1024-aligned (checked at run time, trap otherwise).
 constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximum may lag by up to 2^8
+// ALiBi locality: a key tile is skipped when EVERY probability in it is provably below 2^-50 of its row's largest
+// term (its whole tile adds < 2^-39 relative to the fp32 row sum, 2^15 below fp32 resolution -- the reference's own
+// fp32 softmax, nn/modalities/modules.py:396-399, rounds such terms away as well).
+constexpr float ATT_SKIP_LOG2 = 50.0f;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -145,6 +150,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
     const int L = p.L, D = p.D;
     const int n_kv = (L + 127) >> 7;
+    // Key-tile range [j_begin, j_end) of this query tile. Contiguous sequences with an ALiBi slope: with
+    // B = max|q| max|k| of the head, every score obeys |q.k| * scale2 <= B * scale2, the row's own key (distance 0)
+    // floors the running maximum at -B * scale2, so a key at distance d has exponent <= 2 B scale2 - coef2 d (log2).
+    // Tiles whose nearest key is at least w = (2 B scale2 + ATT_SKIP_LOG2) / coef2 frames away contribute nothing.
+    int j_begin = 0, j_end = n_kv;
+    if (!HAS_POS && p.qk_bound != nullptr) {
+        const float c2 = head_coef(p, h) * LOG2E;
+        if (c2 > 0.f) {
+            const float w = (2.f * p.qk_bound[b * p.H + h] * (p.sm_scale * LOG2E) + ATT_SKIP_LOG2) / c2;
+            if (w < 1.0e6f) {
+                const int wi = (int)w + 1;
+                const int lo = q0 - 127 - wi;  // tile j is kept iff 128 j > lo and 128 j < q0 + 127 + wi
+                j_begin = lo < 0 ? 0 : lo / 128 + 1;
+                const int hi = (q0 + 126 + wi) / 128 + 1;
+                j_end = hi < n_kv ? hi : n_kv;
+            }
+        }
+    }
+    const int n_it = j_end - j_begin;
 
     if (tid == 0) {
         tma_prefetch_desc(&tm);
@@ -178,12 +202,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         mbar_expect_tx(bar_q, 16384);
         tma_load_3d(smem + ATT_SMEM_Q, &tm, bar_q, h * HD, q0, b);
         mbar_expect_tx(&bar_k[0], 16384);
-        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_k[0], D + h * HD, 0, b);
+        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_k[0], D + h * HD, j_begin * 128, b);
         mbar_expect_tx(&bar_v[0], 16384);
-        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_v[0], 2 * D + h * HD, 0, b);
-        if (n_kv > 1) {
+        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_v[0], 2 * D + h * HD, j_begin * 128, b);
+        if (n_it > 1) {
             mbar_expect_tx(&bar_k[1], 16384);
-            tma_load_3d(smem + ATT_SMEM_K + 16384, &tm, &bar_k[1], D + h * HD, 128, b);
+            tma_load_3d(smem + ATT_SMEM_K + 16384, &tm, &bar_k[1], D + h * HD, j_begin * 128 + 128, b);
         }
         mbar_wait(bar_q, 0);
         mbar_wait(&bar_k[0], 0);
@@ -206,8 +230,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     // warps whose 32 query rows all lie beyond L (second q tile of a short sequence) only keep the barriers moving
     const bool warp_active = !TRIM || (q0 + warp * 32) < L;  // TRIM: short sequences (student), skip dead work
 
-    for (int j = 0; j < n_kv; ++j) {
-        const int buf = j & 1;
+    for (int jj = 0; jj < n_it; ++jj) {  // jj: iteration (buffers, barrier phases); j: key tile (positions)
+        const int j = j_begin + jj;
+        const int buf = jj & 1;
         const int k0 = j * 128;
         const bool last = (j == n_kv - 1);
         if (HAS_POS) {
@@ -217,10 +242,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             __syncthreads();
         }
         FT_TR(0);
-        mbar_wait(bar_s, j & 1);
+        mbar_wait(bar_s, jj & 1);
         tc_fence_after();
         FT_TR(1);
-        if (warp == 0 && elect_one() && j + 2 < n_kv) {  // K buffer `buf` is free: S(j) has been computed
+        if (warp == 0 && elect_one() && jj + 2 < n_it) {  // K buffer `buf` is free: S(j) has been computed
             mbar_expect_tx(&bar_k[buf], 16384);
             tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
         }
@@ -283,37 +308,37 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         // every thread holds its scores: the S accumulator is free, so S of the NEXT tile runs on the tensor
         // pipe while this tile's exponentials are computed (it used to be issued after P.V, leaving the CTA
         // waiting a full MMA round trip at the top of every iteration)
-        if (j + 1 < n_kv) {
+        if (jj + 1 < n_it) {
             tc_fence_before();
             __syncthreads();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                mbar_wait(&bar_k[buf ^ 1], ((j + 1) >> 1) & 1);
+                mbar_wait(&bar_k[buf ^ 1], ((jj + 1) >> 1) & 1);
                 tc_fence_after();
                 FT_TR(8);
                 issue_s(buf ^ 1);
                 FT_TR(9);
 #ifdef A2V_ATTN_TRACE
                 if (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 1 && j == 6) {
-                    while (!mbar_try_wait(bar_s, (j + 1) & 1)) {}
+                    while (!mbar_try_wait(bar_s, (jj + 1) & 1)) {}
                     g_ft_trace[10] = clock64();
                 }
 #endif
             }
         }
         // previous P.V done: P smem, V[buf^1] and the O accumulator are ours again
-        if (j > 0) {
-            mbar_wait(bar_o, (j - 1) & 1);
+        if (jj > 0) {
+            mbar_wait(bar_o, (jj - 1) & 1);
             tc_fence_after();
         }
         FT_TR(3);
-        if (warp == 0 && elect_one() && j + 1 < n_kv) {
+        if (warp == 0 && elect_one() && jj + 1 < n_it) {
             mbar_expect_tx(&bar_v[buf ^ 1], 16384);
             tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
         }
         // lazy rescaling of O (in TMEM) and of the running sum
         const bool grow = m_tile > m_run + ATT_RESCALE_THRESHOLD;  // also true on the first tile (m_run = -inf)
-        if (j > 0 && warp_active && __any_sync(0xffffffffu, grow)) {
+        if (jj > 0 && warp_active && __any_sync(0xffffffffu, grow)) {
             const float alpha = grow ? ex2_approx(m_run - m_tile) : 1.0f;
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -377,20 +402,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         if (warp == 0 && elect_one()) {
             tc_fence_after();
             FT_TR(11);
-            mbar_wait(&bar_v[buf], (j >> 1) & 1);
+            mbar_wait(&bar_v[buf], (jj >> 1) & 1);
             FT_TR(12);
             const uint32_t va = smem_u32(smem + ATT_SMEM_V + buf * 16384);
 #pragma unroll
             for (int k = 0; k < 8; ++k)  // 16 keys = 8 packed columns of P per step
                 umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_smem_desc(va + k * 2048, 8192, 1024), idesc_o,
-                             (j > 0 || k > 0) ? 1u : 0u);
+                             (jj > 0 || k > 0) ? 1u : 0u);
             umma_commit(bar_o);
             FT_TR(13);
         }
         FT_TR(6);
     }
 
-    mbar_wait(bar_o, (n_kv - 1) & 1);
+    mbar_wait(bar_o, (n_it - 1) & 1);
     tc_fence_after();
     {
         const float inv_l = 1.0f / l_run;
@@ -416,6 +441,55 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc<256>(tmem_base);
+    }
+}
+
+// bound[b * H + h] = max_i |q_i| * max_j |k_j| (slightly rounded up): the data-dependent part of the ALiBi locality
+// window of attn_fwd_tcgen05_kernel. Eight lanes per row (16 bytes each), grid (H, batch).
+__global__ void __launch_bounds__(256) attn_qk_bound_kernel(const bf16* __restrict__ qkv, float* __restrict__ bound,
+                                                            int L, int H) {
+    __shared__ float red[2][8];
+    const int h = blockIdx.x, b = blockIdx.y, D = H * HD;
+    const int sub = threadIdx.x & 7;
+    float mq = 0.f, mk = 0.f;
+    for (int i0 = 0; i0 < L; i0 += 32) {  // uniform trip count: the shuffles below need every lane of the warp
+        const int i = i0 + (threadIdx.x >> 3);
+        uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = make_uint4(0u, 0u, 0u, 0u);
+        if (i < L) {
+            const bf16* row = qkv + ((long long)b * L + i) * 3 * D + h * HD + sub * 8;
+            vq = *reinterpret_cast<const uint4*>(row);
+            vk = *reinterpret_cast<const uint4*>(row + D);
+        }
+        float sq = 0.f, sk = 0.f;
+        const uint32_t wq[4] = {vq.x, vq.y, vq.z, vq.w}, wk[4] = {vk.x, vk.y, vk.z, vk.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float2 a = unpack_bf16x2(wq[c]), k2 = unpack_bf16x2(wk[c]);
+            sq = fmaf(a.x, a.x, fmaf(a.y, a.y, sq));
+            sk = fmaf(k2.x, k2.x, fmaf(k2.y, k2.y, sk));
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            sk += __shfl_xor_sync(0xffffffffu, sk, o);
+        }
+        mq = fmaxf(mq, sq);
+        mk = fmaxf(mk, sk);
+    }
+    mq = warp_max(mq);
+    mk = warp_max(mk);
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = mq;
+        red[1][threadIdx.x >> 5] = mk;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) {
+            mq = fmaxf(mq, red[0][w]);
+            mk = fmaxf(mk, red[1][w]);
+        }
+        bound[b * H + h] = sqrtf(mq) * sqrtf(mk) * 1.002f;
     }
 }
 
@@ -1177,6 +1251,7 @@ static int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
     p.batch = d->batch; p.L = d->L; p.H = d->H; p.D = d->H * HD;
     p.sm_scale = d->sm_scale; p.drop_p = d->drop_p; p.seed = d->seed;
     p.dout = d->dout; p.dqkv = d->dqkv; p.dalibi_scale = d->dalibi_scale;
+    p.qk_bound = d->qk_bound;
     return A2V_OK;
 }
 
@@ -1192,6 +1267,14 @@ extern "C" int a2v_debug_attn_fwd_trace(long long* out, int n) {
     return (int)cudaMemcpyFromSymbol(out, g_ft_trace, sizeof(long long) * (size_t)(n < 64 ? n : 64));
 }
 #endif
+
+extern "C" int a2v_attn_qk_bound(const void* qkv_bf16, float* bound, int batch, int L, int H, a2v_stream_t stream) {
+    A2V_REQUIRE(qkv_bf16 && bound && batch > 0 && L > 0 && H > 0 && batch <= 65535, "attn_qk_bound: bad arguments");
+    A2V_REQUIRE((reinterpret_cast<uintptr_t>(qkv_bf16) & 15) == 0, "attn_qk_bound: qkv not 16-byte aligned");
+    attn_qk_bound_kernel<<<dim3(H, batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(qkv_bf16), bound, L, H);
+    return a2v_check_launch("attn_qk_bound");
+}
 
 extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     AttnParams p;

@@ -126,6 +126,8 @@ class PretrainEngine:
             self.aweight = torch.from_numpy(a_weight_table(cfg.sample_rate, n_fft)).float().to(self.device)
 
         self._pack_table_s = self._pack_table_t = self._unpack_table = None
+        # full-length (teacher) attention visits only the key tiles ALiBi leaves above 2^-50 (see ops.attn_fwd)
+        self.alibi_locality = True
         self._build_packs()
         self.ctx = None
         self.kernel_launches = 0
@@ -458,7 +460,8 @@ class PretrainEngine:
         s_att, s1, s2 = self._seed(site), self._seed(site + 1), self._seed(site + 2)
         p_att = cfg.attention_dropout if train else 0.0
         ao, lse = ops.attn_fwd(qkv.view(rows, seq, 3 * d), rows, seq, self.H, pos=pos, slopes=self.slopes,
-                               alibi_scale=W.alibi, drop_p=p_att, seed=s_att, need_lse=save is not None)
+                               alibi_scale=W.alibi, drop_p=p_att, seed=s_att, need_lse=save is not None,
+                               skip_far_keys=self.alibi_locality and pos is None)
         pr = self.lin(ao.view(rows * seq, d), W, pre + "attn.proj.weight", bias=f[pre + "attn.proj.bias"])
         c1 = ops.RowLnCfg(d, cfg.norm_eps, drop_b=cfg.encoder_dropout)
         x1, m1, r1 = ops.rowln_fwd(c1, x, pr, f[pre + "norm1.weight"], f[pre + "norm1.bias"], seed_b=s1,

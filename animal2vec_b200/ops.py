@@ -66,6 +66,7 @@ class AttnDesc(C.Structure):
         ("dout", C.c_void_p),
         ("dqkv", C.c_void_p),
         ("dalibi_scale", C.c_void_p),
+        ("qk_bound", C.c_void_p),
     ]
 
 
@@ -111,7 +112,7 @@ def _call(name: str, anchor: torch.Tensor, *args) -> None:
         if name.startswith("a2v_rowln"):
             d = args[0]._obj
             tag = f"{name}[C={d.channels},act={d.act},aff={int(bool(d.gamma))},b={int(bool(d.b))},rows={d.rows}]"
-        elif name.startswith("a2v_attn"):
+        elif name in ("a2v_attn_fwd", "a2v_attn_bwd"):
             d = args[0]._obj
             tag = f"{name}[L={d.L},batch={d.batch}]"
         L.timed_call(tag, lambda: L.check(fn(*args, L.stream_ptr()), name))
@@ -182,9 +183,15 @@ def rowln_bwd(cfg: RowLnCfg, dy, a, b, gamma, beta, act_alpha, act_beta, mean, r
 
 # ----------------------------------------------------------------------------- attention
 def attn_fwd(qkv, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None, drop_p=0.0, seed=0,
-             need_lse=True):
+             need_lse=True, skip_far_keys=False):
+    """``skip_far_keys`` (bf16, contiguous positions, ALiBi slopes given): key tiles whose every probability is provably
+    below 2^-50 of the row maximum are not visited (one extra launch computes max|q| max|k| per head)."""
     assert qkv.is_contiguous() and qkv.shape[-1] == 3 * heads * 64
     out = torch.empty(batch, seq, heads * 64, device=qkv.device, dtype=qkv.dtype)
+    bound = None
+    if skip_far_keys and pos is None and slopes is not None and qkv.dtype == torch.bfloat16 and seq > 256:
+        bound = torch.empty(batch * heads, device=qkv.device, dtype=torch.float32)
+        _call("a2v_attn_qk_bound", qkv, _p(qkv), _p(bound), batch, seq, heads)
     lse = torch.empty(batch, heads, seq, device=qkv.device, dtype=torch.float32) if need_lse else None
     d = AttnDesc()
     d.dtype = L.dtype_code(qkv)
@@ -194,6 +201,7 @@ def attn_fwd(qkv, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None,
     d.alibi_scale_stride = 0 if (alibi_scale is None or alibi_scale.numel() == 1) else 1
     d.sm_scale = 64 ** -0.5
     d.drop_p, d.seed = drop_p, seed
+    d.qk_bound = _p(bound)
     _call("a2v_attn_fwd", qkv, C.byref(d))
     return out, lse
 

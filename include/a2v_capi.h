@@ -310,8 +310,13 @@ typedef struct {
     const void* dout;
     void* dqkv;
     float* dalibi_scale;
+    /* forward, optional (bf16, pos == NULL): (batch*H) values max|q|*max|k| from a2v_attn_qk_bound. With it the
+     * forward skips key tiles that ALiBi pushes below 2^-50 of the row maximum (their sum is far below fp32
+     * resolution; the reference materialises and rounds them away, nn/modalities/modules.py:393-399). */
+    const float* qk_bound;
 } a2v_attn_desc;
 
+int a2v_attn_qk_bound(const void* qkv_bf16, float* bound, int batch, int L, int H, a2v_stream_t stream);
 int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream);
 int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream);
 

@@ -183,6 +183,32 @@ def test_attention_fwd_bwd(dtype, batch, seq, heads, with_pos):
         assert _rel(dsc, sr.grad) < max(gt, 1e-3), (dsc, sr.grad)
 
 
+@pytest.mark.parametrize("qk_scale,seq", [(1.0, 2000), (0.3, 2000), (6.0, 2000), (1.0, 1111), (1.0, 2500)])
+def test_attention_alibi_locality_skip_is_exact(qk_scale, seq):
+    """Full-length (teacher) attention with the ALiBi key-tile window: identical to the full sweep and to fp32 torch
+    math for small, unit and large q/k norms (the window widens with max|q| max|k|; with large norms nothing is
+    skipped), for ragged lengths, with the model's 16 slopes and a zero-scale head (no ALiBi -> no skipping)."""
+    from animal2vec_b200 import ops
+
+    batch, heads = 2, 16
+    d = heads * 64
+    qkv = (torch.randn(batch, seq, 3 * d, device="cuda", generator=_g(1)) * qk_scale).bfloat16()
+    qkv[..., 2 * d:] = torch.randn(batch, seq, d, device="cuda", generator=_g(2)).bfloat16()
+    slopes = torch.tensor([2.0 ** (-0.5 * (h + 1)) for h in range(heads)], device="cuda")
+    scale = torch.rand(heads, device="cuda", generator=_g(3)) + 0.5
+    scale[5] = 0.0
+    full, lse_full = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale)
+    fast, lse_fast = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale, skip_far_keys=True)
+    # P is rounded to bf16 relative to a lazily updated running maximum, which evolves differently when the sweep
+    # starts next to the diagonal: the two results differ by that (decorrelated) rounding noise only -- both sit at the
+    # same distance from fp32 torch math, and the fp32 log-sum-exp agrees to rounding
+    assert _rel(fast, full) < 1e-3, _rel(fast, full)
+    assert _rel(lse_fast, lse_full) < 1e-5
+    ref = _attn_ref(qkv, batch, seq, heads, None, slopes, scale)
+    e_fast, e_full = _rel(fast, ref), _rel(full, ref)
+    assert e_fast < 1e-2 and e_fast < 1.05 * e_full + 1e-4, (e_fast, e_full)
+
+
 def test_attention_dropout_statistics():
     from animal2vec_b200 import ops
 
