@@ -219,7 +219,11 @@ __device__ __forceinline__ void epilogue_chunk_f32_accum(const GemmParams& p, fl
     }
 }
 
-template <int EPI> constexpr bool epi_is_wide() { return EPI >= 0 && (EPI & EPI_GELU) != 0; }
+// The 8-warp epilogue with bf16 staging serves the compile-time variants plain, bias, bias+GELU(+preact) and +residual
+// (the residual rows are prefetched in the TMEM-native layout, thread = row, before the accumulator wait): its shared-memory staging moves half the bytes of the fp32 staging of the 4-warp epilogue, and
+// shared-memory bandwidth is what the epilogue competes for with the MMA operand reads (ncu: the epilogue's stores wait
+// on the short scoreboard of the staged LDS while tcgen05.mma streams 96 B/clk of operands).
+template <int EPI> constexpr bool epi_is_wide() { return EPI >= 0 && (EPI & EPI_DGELU) == 0; }
 
 template <int BLOCK_N, int MODE, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS_WIDE, 1)
@@ -380,7 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int col_base = t.g * p.c_group_stride;
             const long long row_off0 = row_g * p.ldc;
             float* bs = bias_stage + ew * (CPW * 32);  // this warp's CPW chunks of the tile's bias vector
-            {
+            if (EPI & EPI_BIAS) {
                 const int cbase = t.n_tile * BLOCK_N + c_begin * 32;
                 const float* bg = p.bias + col_base + cbase;
                 const int ncols = p.N - cbase;
@@ -391,9 +395,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 __syncwarp();
             }
+            // residual variant: this thread's row of the residual tile (64 bytes per 32-column chunk), every load of the
+            // tile issued NOW so that their latency hides behind the MMAs of the tile
+            constexpr bool RES = (EPI & EPI_RES) != 0;
+            uint4 rsd[RES ? CPW : 1][4];
+            if (RES) {
+                const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + row_off0 + (long long)lane * p.ldc + col_base;
+#pragma unroll
+                for (int cc = 0; cc < CPW; ++cc) {
+                    const int col0 = t.n_tile * BLOCK_N + (c_begin + cc) * 32;
+                    const bool ok = lane < rows_ok && (c_begin + cc) < BLOCK_N / 32 && col0 < p.N;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        rsd[RES ? cc : 0][j] = ok ? __ldg(reinterpret_cast<const uint4*>(rp + col0) + j) : make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
             mbar_wait(&tfull_bar[as], aphase);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll(RES ? CPW : 1)
             for (int cc = 0; cc < CPW; ++cc) {
                 const int c = c_begin + cc;
                 const int col0 = t.n_tile * BLOCK_N + c * 32;
@@ -404,17 +423,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 float x[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 bv = *reinterpret_cast<const float4*>(bs + cc * 32 + 4 * j);
+                    const float4 bv = (EPI & EPI_BIAS) ? *reinterpret_cast<const float4*>(bs + cc * 32 + 4 * j)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                     x[4 * j] = fmaf(__uint_as_float(raw[4 * j]), p.alpha, bv.x);
                     x[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), p.alpha, bv.y);
                     x[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), p.alpha, bv.z);
                     x[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), p.alpha, bv.w);
                 }
+                if (RES) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 rv = rsd[RES ? cc : 0][j];
+                        const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
+                        const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
+                        x[8 * j] += r0.x; x[8 * j + 1] += r0.y; x[8 * j + 2] += r1.x; x[8 * j + 3] += r1.y;
+                        x[8 * j + 4] += r2.x; x[8 * j + 5] += r2.y; x[8 * j + 6] += r3.x; x[8 * j + 7] += r3.y;
+                    }
+                }
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass == 0 && !(EPI & EPI_PREACT)) continue;
                     bf16* dst = reinterpret_cast<bf16*>(pass == 0 ? p.preact : p.c);
-                    if (pass == 1) {
+                    if (pass == 1 && (EPI & EPI_GELU)) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) x[i] = gelu_tanh_fast(x[i]);
                     }
@@ -737,10 +767,11 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         if (m == 0 || m == EPI_BIAS || m == (EPI_BIAS | EPI_GELU | EPI_PREACT) || m == (EPI_BIAS | EPI_GELU) ||
             m == EPI_DGELU || m == EPI_RES)
             epi = m;
-        // the 8-warp GELU epilogue moves whole 16-byte column groups
-        if (epi >= 0 && (epi & EPI_GELU) &&
+        // the 8-warp epilogue moves whole 16-byte column groups
+        if (epi >= 0 && (epi & EPI_DGELU) == 0 &&
             (d->N % 32 != 0 || d->ldc % 8 != 0 || d->c_group_stride % 8 != 0 ||
              (reinterpret_cast<uintptr_t>(d->c) & 15) != 0 || (reinterpret_cast<uintptr_t>(d->preact) & 15) != 0 ||
+             (reinterpret_cast<uintptr_t>(d->residual) & 15) != 0 ||
              (reinterpret_cast<uintptr_t>(d->bias) & 15) != 0))
             epi = -1;
     }
