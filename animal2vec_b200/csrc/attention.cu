@@ -40,7 +40,7 @@ struct AttnParams {
     const void* dout;
     void* dqkv;
     float* dalibi_scale;
-    const float* qk_bound;  // optional, (batch * H): max |q| * max |k| of the head (see attn_qk_bound_kernel)
+    const float* qk_bound;  // optional, (batch * H) x {max |q|^2, max |k|^2} of the head (see attn_qk_bound_kernel)
 };
 
 __device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
@@ -158,7 +158,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     if (!HAS_POS && p.qk_bound != nullptr) {
         const float c2 = head_coef(p, h) * LOG2E;
         if (c2 > 0.f) {
-            const float w = (2.f * p.qk_bound[b * p.H + h] * (p.sm_scale * LOG2E) + ATT_SKIP_LOG2) / c2;
+            const float2 b2 = reinterpret_cast<const float2*>(p.qk_bound)[b * p.H + h];  // max|q|^2, max|k|^2
+            const float qk = sqrtf(b2.x) * sqrtf(b2.y) * 1.002f;
+            const float w = (2.f * qk * (p.sm_scale * LOG2E) + ATT_SKIP_LOG2) / c2;
             if (w < 1.0e6f) {
                 const int wi = (int)w + 1;
                 const int lo = q0 - 127 - wi;  // tile j is kept iff 128 j > lo and 128 j < q0 + 127 + wi
@@ -444,16 +446,20 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     }
 }
 
-// bound[b * H + h] = max_i |q_i| * max_j |k_j| (slightly rounded up): the data-dependent part of the ALiBi locality
-// window of attn_fwd_tcgen05_kernel. Eight lanes per row (16 bytes each), grid (H, batch).
-__global__ void __launch_bounds__(256) attn_qk_bound_kernel(const bf16* __restrict__ qkv, float* __restrict__ bound,
+// bound2[(b * H + h) * 2 + {0, 1}] = max_i |q_i|^2, max_j |k_j|^2: the data-dependent part of the ALiBi locality window
+// of attn_fwd_tcgen05_kernel. Eight lanes per row (16 bytes each), grid (H, batch, row chunks); the chunks combine with
+// an integer atomicMax (non-negative floats order like their bit patterns); the caller zero-fills the buffer.
+constexpr int QKB_CHUNK = 256;  // rows per block
+__global__ void __launch_bounds__(256) attn_qk_bound_kernel(const bf16* __restrict__ qkv, float* __restrict__ bound2,
                                                             int L, int H) {
     __shared__ float red[2][8];
     const int h = blockIdx.x, b = blockIdx.y, D = H * HD;
     const int sub = threadIdx.x & 7;
+    const int r0 = blockIdx.z * QKB_CHUNK;
     float mq = 0.f, mk = 0.f;
-    for (int i0 = 0; i0 < L; i0 += 32) {  // uniform trip count: the shuffles below need every lane of the warp
-        const int i = i0 + (threadIdx.x >> 3);
+#pragma unroll
+    for (int it = 0; it < QKB_CHUNK / 32; ++it) {  // uniform trip count: the shuffles below need every lane of the warp
+        const int i = r0 + it * 32 + (threadIdx.x >> 3);
         uint4 vq = make_uint4(0u, 0u, 0u, 0u), vk = make_uint4(0u, 0u, 0u, 0u);
         if (i < L) {
             const bf16* row = qkv + ((long long)b * L + i) * 3 * D + h * HD + sub * 8;
@@ -489,7 +495,8 @@ __global__ void __launch_bounds__(256) attn_qk_bound_kernel(const bf16* __restri
             mq = fmaxf(mq, red[0][w]);
             mk = fmaxf(mk, red[1][w]);
         }
-        bound[b * H + h] = sqrtf(mq) * sqrtf(mk) * 1.002f;
+        atomicMax(reinterpret_cast<int*>(bound2) + (b * H + h) * 2, __float_as_int(mq));
+        atomicMax(reinterpret_cast<int*>(bound2) + (b * H + h) * 2 + 1, __float_as_int(mk));
     }
 }
 
@@ -1271,7 +1278,7 @@ extern "C" int a2v_debug_attn_fwd_trace(long long* out, int n) {
 extern "C" int a2v_attn_qk_bound(const void* qkv_bf16, float* bound, int batch, int L, int H, a2v_stream_t stream) {
     A2V_REQUIRE(qkv_bf16 && bound && batch > 0 && L > 0 && H > 0 && batch <= 65535, "attn_qk_bound: bad arguments");
     A2V_REQUIRE((reinterpret_cast<uintptr_t>(qkv_bf16) & 15) == 0, "attn_qk_bound: qkv not 16-byte aligned");
-    attn_qk_bound_kernel<<<dim3(H, batch), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    attn_qk_bound_kernel<<<dim3(H, batch, ceil_div(L, QKB_CHUNK)), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const bf16*>(qkv_bf16), bound, L, H);
     return a2v_check_launch("attn_qk_bound");
 }

@@ -42,6 +42,7 @@ struct ConvSlabParams {
     int m_tiles;     // ceil(T / CS_SUPER_M)
     int num_tiles;
     int bo_mode;
+    int fast_store;  // bf16 output, 8-column groups 16-byte aligned: bf16 staging + 16-byte stores
 };
 
 __device__ __forceinline__ uint64_t umma_smem_desc_bo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_off) {
@@ -216,6 +217,45 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (CS_MT * 64) + mt * 64 + c * 32, raw);
                     tmem_ld_wait();
                     if (c * 32 >= p.ng) break;
+                    if (p.fast_store) {
+                        // bf16 staging (half the shared-memory bytes of the fp32 staging below; this kernel is bound by
+                        // shared-memory operand bandwidth): bias added in the TMEM-native layout (thread = row), packed,
+                        // transposed through an 80-byte-pitch row, 16-byte stores (8 rows x 64 contiguous bytes each)
+                        const uint32_t st16 = smem_u32(reinterpret_cast<uint8_t*>(epi_stage) + (warp - 2) * (32 * 80));
+                        const float* bp = p.bias != nullptr ? p.bias + g * p.y_group_cols + c * 32 : nullptr;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(raw[8 * j + i]);
+                            if (bp != nullptr && c * 32 + 8 * j < p.ng) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + 8 * j));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + 8 * j) + 1);
+                                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st16 + lane * 80 + 16 * j),
+                                         "r"(pack_bf16x2(x[0], x[1])), "r"(pack_bf16x2(x[2], x[3])),
+                                         "r"(pack_bf16x2(x[4], x[5])), "r"(pack_bf16x2(x[6], x[7]))
+                                         : "memory");
+                        }
+                        __syncwarp();
+                        const int rrow = lane & 7, rchunk = lane >> 3;
+                        bf16* yb = reinterpret_cast<bf16*>(p.y) + row_off0 + g * p.y_group_cols + c * 32 + 8 * rchunk;
+                        const bool col_ok = c * 32 + 8 * rchunk + 8 <= p.ng;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int r = rrow + 8 * i;
+                            uint4 v4;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(v4.x), "=r"(v4.y), "=r"(v4.z), "=r"(v4.w)
+                                         : "r"(st16 + r * 80 + 16 * rchunk)
+                                         : "memory");
+                            if (r < rows_ok && col_ok) *reinterpret_cast<uint4*>(yb + (long long)r * p.ldy) = v4;
+                        }
+                        __syncwarp();
+                        continue;
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + (lane * CS_EPI_PITCH + 4 * j) * 4),
@@ -484,6 +524,8 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     p.m_tiles = ceil_div(d->T, CS_SUPER_M);
     p.num_tiles = p.m_tiles * d->batch * d->groups;
     p.bo_mode = d->reserved;
+    p.fast_store = !p.y_f32 && d->ng % 8 == 0 && d->ldy % 8 == 0 && d->y_group_cols % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d->y) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0;
     CUtensorMap tx, tw;
     int rc;
     if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, p.slab_rows / 2, "x")) != A2V_OK) return rc;

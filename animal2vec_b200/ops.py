@@ -190,7 +190,7 @@ def attn_fwd(qkv, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None,
     out = torch.empty(batch, seq, heads * 64, device=qkv.device, dtype=qkv.dtype)
     bound = None
     if skip_far_keys and pos is None and slopes is not None and qkv.dtype == torch.bfloat16 and seq > 256:
-        bound = torch.empty(batch * heads, device=qkv.device, dtype=torch.float32)
+        bound = torch.zeros(batch * heads * 2, device=qkv.device, dtype=torch.float32)
         _call("a2v_attn_qk_bound", qkv, _p(qkv), _p(bound), batch, seq, heads)
     lse = torch.empty(batch, heads, seq, device=qkv.device, dtype=torch.float32) if need_lse else None
     d = AttnDesc()

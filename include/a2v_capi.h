@@ -310,7 +310,8 @@ typedef struct {
     const void* dout;
     void* dqkv;
     float* dalibi_scale;
-    /* forward, optional (bf16, pos == NULL): (batch*H) values max|q|*max|k| from a2v_attn_qk_bound. With it the
+    /* forward, optional (bf16, pos == NULL): (batch*H) pairs {max|q|^2, max|k|^2} from a2v_attn_qk_bound (which
+     * accumulates with atomic max into a buffer the caller zero-fills). With it the
      * forward skips key tiles that ALiBi pushes below 2^-50 of the row maximum (their sum is far below fp32
      * resolution; the reference materialises and rounds them away, nn/modalities/modules.py:393-399). */
     const float* qk_bound;
