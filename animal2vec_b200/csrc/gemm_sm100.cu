@@ -9,6 +9,7 @@
 // Two operand modes (see include/a2v_capi.h):
 //   NT : A, B K-major.  Tap loop over shifted A rows = stride-1 (grouped) conv1d.
 //   TN : A, B MN-major. Reduction over (batch, rows) = weight gradients, optional split-K.
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
@@ -676,6 +677,18 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     return a2v_check_launch("gemm_tcgen05_kernel");
 }
 
+int gemm2cta_try(const a2v_gemm_desc* d, cudaStream_t st);  // gemm2_sm100.cu
+
+// CTA-pair kernel for the plain Linear shapes: on unless A2V_GEMM_2CTA=0
+static bool gemm2cta_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("A2V_GEMM_2CTA");
+        on = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return on == 1;
+}
+
 }  // namespace a2v
 
 using namespace a2v;
@@ -699,6 +712,10 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
                 "gemm: ldc / group / tap strides must keep 16-byte alignment");
     A2V_REQUIRE((reinterpret_cast<uintptr_t>(d->c) & 15) == 0, "gemm: C not 16-byte aligned");
 
+    if (gemm2cta_enabled()) {
+        const int rc2 = gemm2cta_try(d, reinterpret_cast<cudaStream_t>(stream));
+        if (rc2 >= 0) return rc2;
+    }
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.mode = d->mode;
