@@ -307,11 +307,183 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// TN product of a CTA pair (weight gradients of the same Linears):  out[m, n] += alpha * sum_r a[r, m] * b[r, n],
+// fp32 out, split over the reduction rows with atomic accumulation. Both operands are MN-major (64-row k-blocks of
+// 64-column boxes); each CTA holds 128 of the pair tile's 256 M columns and 128 of its 256 N columns. The epilogue adds
+// straight out of the TMEM-native layout (thread = output row, 16-byte vector reductions): no shared-memory staging.
+// ------------------------------------------------------------------------------------------------------------------
+struct Gemm2TnParams {
+    int M, N, kblocks, per_split;
+    int n_tiles, m_tiles2, splits, num_tiles;
+    float* c;
+    long long ldc;
+    float alpha;
+};
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2cta_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2TnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + G2_STAGES;
+    uint64_t* tfull_bar = empty_bar + G2_STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < G2_STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 16);
+        }
+        mbar_fence_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (n_tile, m2, split); k-block range of the split
+    auto decode = [&](int tile, int& n_tile, int& m2, int& kb0, int& kb1) {
+        n_tile = tile % p.n_tiles;
+        tile /= p.n_tiles;
+        m2 = tile % p.m_tiles2;
+        const int split = tile / p.m_tiles2;
+        kb0 = split * p.per_split;
+        kb1 = kb0 + p.per_split;
+        kb1 = kb1 < p.kblocks ? kb1 : p.kblocks;
+        if (kb1 < kb0) kb1 = kb0;
+    };
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+                int n_tile, m2, kb0, kb1;
+                decode(tile, n_tile, m2, kb0, kb1);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+                    uint8_t* sb = sa + G2_A_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        tma_load_3d_pair(sa + i * 8192, &tmA, &full_bar[stage], m2 * 256 + (int)rank * 128 + i * 64, kb * G2_BK, 0);
+                        tma_load_3d_pair(sb + i * 8192, &tmB, &full_bar[stage], n_tile * 256 + (int)rank * 128 + i * 64, kb * G2_BK, 0);
+                    }
+                    if (++stage == G2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(256, 256, true, true);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+                int n_tile, m2, kb0, kb1;
+                decode(tile, n_tile, m2, kb0, kb1);
+                mbar_wait_cluster(&tempty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * G2_BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + stage * G2_STAGE_BYTES);
+                    const uint32_t b_base = a_base + G2_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < G2_BK / 16; ++k)
+                        umma2_bf16(tmem_d, umma_smem_desc(a_base + k * (16 * 128), 8192, 1024),
+                                   umma_smem_desc(b_base + k * (16 * 128), 8192, 1024), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    umma2_commit(&empty_bar[stage]);
+                    if (++stage == G2_STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma2_commit(&tfull_bar[as]);
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int ew = warp - 2;
+        const int c_begin = (ew >> 2) * 4;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+            int n_tile, m2, kb0, kb1;
+            decode(tile, n_tile, m2, kb0, kb1);
+            const int row = m2 * 256 + (int)rank * 128 + q * 32 + lane;  // this thread's output row
+            float* crow = p.c + (long long)row * p.ldc + n_tile * 256 + c_begin * 32;
+            mbar_wait(&tfull_bar[as], aphase);
+            tc_fence_after();
+            if (kb1 > kb0) {
+#pragma unroll 1
+                for (int cc = 0; cc < 4; ++cc) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * G2_BN + (c_begin + cc) * 32, raw);
+                    tmem_ld_wait();
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            atomicAdd(reinterpret_cast<float4*>(crow + cc * 32) + j,
+                                      make_float4(__uint_as_float(raw[4 * j]) * p.alpha, __uint_as_float(raw[4 * j + 1]) * p.alpha,
+                                                  __uint_as_float(raw[4 * j + 2]) * p.alpha, __uint_as_float(raw[4 * j + 3]) * p.alpha));
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+            if (++as == 2) {
+                as = 0;
+                aphase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int g2_make_map(CUtensorMap* m, const a2v_operand& o) {
+static int g2_make_map(CUtensorMap* m, const a2v_operand& o, int box_rows = 128) {
     static EncodeTiledFn3 fn = nullptr;
     if (fn == nullptr) {
         void* sym = nullptr;
@@ -321,7 +493,7 @@ static int g2_make_map(CUtensorMap* m, const a2v_operand& o) {
     }
     cuuint64_t dims[3] = {(cuuint64_t)o.dim0, (cuuint64_t)o.dim1, 1};
     cuuint64_t strides[2] = {(cuuint64_t)o.stride1 * 2, (cuuint64_t)o.stride1 * o.dim1 * 2};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -363,9 +535,73 @@ static int g2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Pa
     return a2v_check_launch("gemm2cta_kernel");
 }
 
+static int g2_try_tn(const a2v_gemm_desc* d, cudaStream_t st) {
+    if (d->taps != 1 || d->batch != 1 || d->groups != 1 || d->a_tap_cols != 0 || d->c_dtype != A2V_F32) return -1;
+    if (!d->out_atomic || d->M % 256 != 0 || d->N % 256 != 0 || d->ldc % 4 != 0 || d->red_rows < 64 * 16) return -1;
+    if (d->a_row_off != 0 || d->b_row_off != 0 || d->c_row_off != 0) return -1;
+    if (d->a.dim2 != 1 || d->b.dim2 != 1 || d->a.stride1 % 8 != 0 || d->b.stride1 % 8 != 0) return -1;
+    if ((reinterpret_cast<uintptr_t>(d->a.ptr) | reinterpret_cast<uintptr_t>(d->b.ptr) | reinterpret_cast<uintptr_t>(d->c)) & 15)
+        return -1;
+    Gemm2TnParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = d->M; p.N = d->N;
+    p.kblocks = ceil_div(d->red_rows, G2_BK);
+    p.n_tiles = d->N / 256;
+    p.m_tiles2 = d->M / 256;
+    const int tiles = p.n_tiles * p.m_tiles2;
+    const int pairs_total = a2v_num_sms() / 2;
+    // split count (<= 16, at least 8 k-blocks each) that fills whole waves of CTA pairs best
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 16; ++s) {
+        if (p.kblocks / s < 8 && s > 1) break;
+        const int inst = tiles * s;
+        const double eff = (double)inst / ((double)ceil_div(inst, pairs_total) * pairs_total);
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    p.per_split = ceil_div(p.kblocks, best);
+    p.splits = ceil_div(p.kblocks, p.per_split);
+    p.num_tiles = tiles * p.splits;
+    p.c = reinterpret_cast<float*>(d->c);
+    p.ldc = d->ldc;
+    p.alpha = d->alpha;
+    CUtensorMap ta, tb;
+    if (g2_make_map(&ta, d->a, 64) != 0 || g2_make_map(&tb, d->b, 64) != 0) return -1;
+    auto kern = gemm2cta_tn_kernel;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) {
+            a2v_set_error("gemm(2cta, tn): cudaFuncSetAttribute failed");
+            return A2V_ERR_CUDA;
+        }
+        configured = true;
+    }
+    int pairs = pairs_total < p.num_tiles ? pairs_total : p.num_tiles;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(G2_THREADS);
+    cfg.dynamicSmemBytes = G2_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p);
+    if (e != cudaSuccess) {
+        a2v_set_error("gemm(2cta, tn): launch failed: %s", cudaGetErrorString(e));
+        return A2V_ERR_CUDA;
+    }
+    return a2v_check_launch("gemm2cta_tn_kernel");
+}
+
 // Returns -1 when the descriptor is not a plain 2-D bf16 Linear the pair kernel handles (the caller then takes the
 // one-CTA kernel), otherwise the launch status.
 int gemm2cta_try(const a2v_gemm_desc* d, cudaStream_t st) {
+    if (d->mode == 1) return g2_try_tn(d, st);
     if (d->mode != 0 || d->taps != 1 || d->batch != 1 || d->groups != 1 || d->c_dtype != A2V_BF16) return -1;
     if (d->out_atomic || d->out_accumulate || d->dgelu_u != nullptr) return -1;
     if (d->block_n != 256 || d->N % G2_BN != 0 || d->k_per_tap % G2_BK != 0 || d->M < 4 * G2_BM) return -1;

@@ -41,3 +41,14 @@ for (m, n, k) in [(42624, 4096, 1024), (42624, 1024, 4096), (48000, 3072, 1024),
     tt = bench(lambda: torch.matmul(a, w.t(), out=out))
     f = 2 * m * n * k / 1e9
     print((m, n, k), f"plain {f/t0:.0f}  bias {f/t1:.0f}  gelu+preact {f/t2:.0f}  residual {f/t3:.0f}  cuBLAS {f/tt:.0f} TFLOP/s", flush=True)
+# TN (weight gradient) products
+for (r, m, n) in [(5000, 256, 256), (42624, 1024, 1024), (42624, 4096, 1024), (42624, 1024, 4096), (42624, 3072, 1024)]:
+    a = torch.randn(r, m, device="cuda", generator=g).bfloat16()
+    b = torch.randn(r, n, device="cuda", generator=g).bfloat16()
+    out = torch.ones(m, n, device="cuda")
+    gemm.gemm_tn(a, b, out)
+    ref = 1 + a.float().t() @ b.float()
+    e = rel(out, ref)
+    out.zero_()
+    t = bench(lambda: gemm.gemm_tn(a, b, out))
+    print("tn", (r, m, n), f"rel {e:.2e}", "OK" if e < 1e-5 else "FAIL", f"{2 * r * m * n / t / 1e9:.0f} TFLOP/s", flush=True)
