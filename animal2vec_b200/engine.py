@@ -128,6 +128,8 @@ class PretrainEngine:
         self._pack_table_s = self._pack_table_t = self._unpack_table = None
         # full-length (teacher) attention visits only the key tiles ALiBi leaves above 2^-50 (see ops.attn_fwd)
         self.alibi_locality = True
+        # the im2col operands of the strided feature-extractor convs (85 MB per clip) are kept for the weight gradients
+        self.keep_im2col = True
         self._build_packs()
         self.ctx = None
         self.kernel_launches = 0
@@ -419,13 +421,15 @@ class PretrainEngine:
                 tout = (tin + 2 * pad - k) // st + 1
                 col = ops.im2col(xin, k, st, pad, tout)
                 y = self.lin(col, W, n)
-                del col
+                if not (save and self.keep_im2col):
+                    col = None
             else:
+                col = None
                 y = self.conv(xin, W, n, taps=k, pad=(k - 1) // 2, groups=1)  # padding="same"
             cfg_i = ops.RowLnCfg(ch, 1e-5, act=1)
             act, m, r = ops.rowln_fwd(cfg_i, y, None, W.f32[le + f"{i}.2.1.weight"], W.f32[le + f"{i}.2.1.bias"],
                                       save_stats=save)
-            fe.append(SimpleNamespace(y=y, m=m, r=r, a=act, cfg=cfg_i))
+            fe.append(SimpleNamespace(y=y, m=m, r=r, a=act, cfg=cfg_i, col=col))
             if not save:
                 fe[-2] = None
         clast = self.layers[-1][0]
@@ -743,9 +747,10 @@ class PretrainEngine:
             if st > 1:
                 pad = int(math.ceil(st / 2))
                 tout = dy.shape[1]
-                col = ops.im2col(xin, k, st, pad, tout)
+                col = s.col if s.col is not None else ops.im2col(xin, k, st, pad, tout)
                 self.wgrad(dy, col, self.gpacked[n + "|F"])
                 del col
+                s.col = None
                 dcol = self.lin(dy, W, n, dgrad=True)
                 da = ops.col2im(dcol.view(b, tout, k * cinp), k, st, pad, tin)
                 del dcol

@@ -298,7 +298,7 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": 16,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM / implicit-conv launches)",
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels: gemm2cta (CTA pairs, block Linears) + gemm_tcgen05 (all other GEMM / strided-conv launches)",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": None,
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",

@@ -156,3 +156,27 @@ def test_conv_slab_wgrad(bsz, t, ng, groups, taps, pad):
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
     gemm.conv_slab_wgrad(dy, x, out, taps=taps, pad=pad, groups=groups)  # accumulates
     assert _rel(out, 2 * ref) < 1e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(513, 256, 64), (1500, 512, 320), (4000, 1024, 1024)])
+def test_cta_pair_gemm_shapes_and_epilogues(m, n, k):
+    """Shapes the CTA-pair (cta_group::2) kernels take (N a multiple of 256, K of 64): ragged M (the second CTA of the last
+    pair partly or wholly out of range), every compile-time epilogue, and the TN weight-gradient product."""
+    from animal2vec_b200 import gemm
+
+    a, w = _randn(m, k, seed=11), _randn(n, k, scale=0.05, seed=12)
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda").bfloat16()
+    u = a.float() @ w.float().t()
+    pre = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    assert _rel(gemm.gemm_nt(a, w), u) < 4e-3
+    assert _rel(gemm.gemm_nt(a, w, bias=bias, alpha=0.5), 0.5 * u + bias) < 4e-3
+    assert _rel(gemm.gemm_nt(a, w, bias=bias, act=1), F.gelu(u + bias)) < 5e-3
+    assert _rel(gemm.gemm_nt(a, w, bias=bias, act=1, preact=pre), F.gelu(u + bias)) < 5e-3 and _rel(pre, u + bias) < 4e-3
+    assert _rel(gemm.gemm_nt(a, w, residual=res), u + res.float()) < 4e-3
+    # TN: out (n_a, n_b) += a^T b over the m rows
+    b2 = _randn(m, 256, seed=13)
+    a2 = _randn(m, n, seed=14)
+    out = torch.ones(n, 256, device="cuda")
+    gemm.gemm_tn(a2, b2, out)
+    assert _rel(out, 1 + a2.float().t() @ b2.float()) < 1e-5

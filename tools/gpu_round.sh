@@ -11,8 +11,8 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --batch $B > gpurun_out/ncu_bench.log 2>&1
 python tools/launch_shares.py gpurun_out/launches.csv 50 > gpurun_out/launch_shares.md 2>&1; head -8 gpurun_out/launch_shares.md
 # full capture: skip the priming + first warm-up step, then 1 launch in 7 of the GEMM / attention / conv / LN kernels
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05|attn_fwd|attn_bwd|slab|resln|rowln_gelu" \
-  --launch-skip 1500 --launch-count 16 --kill on -f -o gpurun_out/r1_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 16 \
+timeout 500 ncu --set full --clock-control none --import-source on -k regex:"gemm2cta|gemm_tcgen05|attn_fwd|attn_bwd|slab|resln|rowln_gelu" \
+  --launch-skip 1500 --launch-count 14 --kill on -f -o gpurun_out/r1_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --batch 16 \
   > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log | cut -c1-300
 ls -la gpurun_out | head -30
