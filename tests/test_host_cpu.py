@@ -209,3 +209,52 @@ def test_unsupported_variants_fail_loudly():
     with pytest.raises(NotImplementedError):
         PretrainEngine._check_supported(c)
     PretrainEngine._check_supported(Cfg.shipped_large())  # the shipped recipe itself is supported
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """Every descriptor struct of include/a2v_capi.h, compiled by gcc, has the same size and field offsets as its ctypes
+    mirror (fields compared in declaration order) -- the C-ABI boundary is plain data, so this is the whole contract."""
+    import ctypes
+    import re
+    import subprocess
+
+    from animal2vec_b200 import lib as L
+    from animal2vec_b200 import ops
+
+    mirrors = {"a2v_operand": L.Operand, "a2v_gemm_desc": L.GemmDesc, "a2v_conv_desc": L.ConvDesc,
+               "a2v_rowln_desc": ops.RowLnDesc, "a2v_attn_desc": ops.AttnDesc, "a2v_relayout_item": ops.RelayoutItem}
+    hdr = open(os.path.join(ROOT, "include", "a2v_capi.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "a2v_capi.h"', "int main(void) {"]
+    fields = {}
+    for name in mirrors:
+        end = re.search(r"\}\s*" + name + r"\s*;", hdr_nc)
+        assert end, name
+        start = hdr_nc.rfind("typedef struct {", 0, end.start())
+        body = hdr_nc[start + len("typedef struct {"):end.start()]
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                ident = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[[^\]]*\])?\s*$", part.strip())
+                assert ident, (name, decl)
+                names.append(ident[0])
+        fields[name] = names
+        prog.append(f'  printf("{name} %zu", sizeof({name}));')
+        for f in names:
+            prog.append(f'  printf(" %zu", offsetof({name}, {f}));')
+        prog.append('  printf("\\n");')
+    prog += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        cls = mirrors[name]
+        assert ctypes.sizeof(cls) == int(size), (name, ctypes.sizeof(cls), size)
+        py_offs = [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert py_offs == [int(o) for o in offs], (name, py_offs, offs, fields[name])
