@@ -12,10 +12,10 @@
 //   attn_fwd_tcgen05_kernel : bf16, flash-style. S = Q K^T and O_j = P V_j run on tcgen05 with
 //                             TMEM accumulators, Q/K/V tiles arrive by TMA, one thread per query row
 //                             does the online softmax straight out of TMEM (no shuffles).
-//   attn_bwd_wmma_kernel    : bf16, student shapes (L <= 160 kept tokens): whole head resident in
-//                             shared memory, mma.sync via wmma.
+//   attn_bwd_tcgen05_kernel : bf16, student shapes (L <= 160 kept tokens): persistent per head, whole head resident
+//                             in shared memory, all five products on tcgen05 with TMEM accumulators.
+//   attn_qk_bound_kernel    : max |q|, max |k| per head (the data-dependent part of the ALiBi key-tile window).
 //   attn_*_ref_kernel       : fp32 CUDA-core kernels for the fp32 validation mode.
-#include <mma.h>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
 
@@ -500,174 +500,7 @@ __global__ void __launch_bounds__(256) attn_qk_bound_kernel(const bf16* __restri
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// backward, shared-memory resident head (student: L <= 160), wmma bf16
-// ------------------------------------------------------------------------------------------
-constexpr int BWD_LMAX = 160;
-constexpr int BWD_LD = 72;    // leading dimension of the (L x 64) operand tiles
-constexpr int BWD_SCR = 20;   // leading dimension of the fp32 16x16 scratch tiles
-
-__global__ void __launch_bounds__(256, 1) attn_bwd_wmma_kernel(const AttnParams p) {
-    using namespace nvcuda;
-    extern __shared__ __align__(128) uint8_t smem_b[];
-    const int L = p.L, D = p.D, h = blockIdx.x, b = blockIdx.y;
-    const int LP = (L + 15) & ~15;
-    const int ldp = LP + 8;
-    bf16* sQ = reinterpret_cast<bf16*>(smem_b);
-    bf16* sK = sQ + LP * BWD_LD;
-    bf16* sV = sK + LP * BWD_LD;
-    bf16* sdO = sV + LP * BWD_LD;
-    bf16* sPd = sdO + LP * BWD_LD;
-    bf16* sdS = sPd + LP * ldp;
-    float* scr = reinterpret_cast<float*>(sdS + LP * ldp);  // 8 warps x 2 x 16 x BWD_SCR
-    float* s_lse = scr + 8 * 2 * 16 * BWD_SCR;
-    float* s_delta = s_lse + LP;
-    int* s_pos = reinterpret_cast<int*>(s_delta + LP);
-    __shared__ float s_dc[8];
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long bh = (long long)b * p.H + h;
-    const bf16* qkv = reinterpret_cast<const bf16*>(p.qkv);
-    const bf16* dout = reinterpret_cast<const bf16*>(p.dout);
-    const bf16* outp = reinterpret_cast<const bf16*>(p.out);
-
-    // ---- stage 0: load operands (8 bf16 = 16 B per access), zero the padding rows
-    for (int e = tid; e < LP * 8; e += 256) {
-        const int i = e >> 3, c8 = (e & 7) * 8;
-        uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, g = q;
-        if (i < L) {
-            const bf16* row = qkv + ((long long)b * L + i) * 3 * D + h * HD + c8;
-            q = *reinterpret_cast<const uint4*>(row);
-            k = *reinterpret_cast<const uint4*>(row + D);
-            v = *reinterpret_cast<const uint4*>(row + 2 * D);
-            g = *reinterpret_cast<const uint4*>(dout + ((long long)b * L + i) * D + h * HD + c8);
-        }
-        *reinterpret_cast<uint4*>(sQ + i * BWD_LD + c8) = q;
-        *reinterpret_cast<uint4*>(sK + i * BWD_LD + c8) = k;
-        *reinterpret_cast<uint4*>(sV + i * BWD_LD + c8) = v;
-        *reinterpret_cast<uint4*>(sdO + i * BWD_LD + c8) = g;
-    }
-    for (int i = tid; i < LP; i += 256) {
-        float dl = 0.f;
-        if (i < L) {
-            const bf16* go = dout + ((long long)b * L + i) * D + h * HD;
-            const bf16* oo = outp + ((long long)b * L + i) * D + h * HD;
-            for (int d = 0; d < HD; d += 4) {
-                float a[4], c[4];
-                load4(go + d, a);
-                load4(oo + d, c);
-                dl += a[0] * c[0] + a[1] * c[1] + a[2] * c[2] + a[3] * c[3];
-            }
-            s_lse[i] = p.lse[bh * L + i];
-            s_pos[i] = p.pos != nullptr ? p.pos[(long long)b * L + i] : i;
-        } else {
-            s_lse[i] = 0.f;
-            s_pos[i] = 0;
-        }
-        s_delta[i] = dl;
-    }
-    __syncthreads();
-
-    const float coef = head_coef(p, h);
-    const float inv_keep = p.drop_p > 0.f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-    const int nt = LP >> 4;
-    float* scr_s = scr + warp * 2 * 16 * BWD_SCR;
-    float* scr_d = scr_s + 16 * BWD_SCR;
-    float dc_part = 0.f;
-
-    // ---- stage 1: S and dP tiles -> P*keep (bf16) and dS (bf16)
-    for (int tile = warp; tile < nt * nt; tile += 8) {
-        const int ti = tile / nt, tj = tile - ti * nt;
-        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc_s, acc_d;
-        wmma::fill_fragment(acc_s, 0.f);
-        wmma::fill_fragment(acc_d, 0.f);
-#pragma unroll
-        for (int k = 0; k < HD; k += 16) {
-            wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::col_major> fb;
-            wmma::load_matrix_sync(fa, sQ + ti * 16 * BWD_LD + k, BWD_LD);
-            wmma::load_matrix_sync(fb, sK + tj * 16 * BWD_LD + k, BWD_LD);
-            wmma::mma_sync(acc_s, fa, fb, acc_s);
-            wmma::load_matrix_sync(fa, sdO + ti * 16 * BWD_LD + k, BWD_LD);
-            wmma::load_matrix_sync(fb, sV + tj * 16 * BWD_LD + k, BWD_LD);
-            wmma::mma_sync(acc_d, fa, fb, acc_d);
-        }
-        wmma::store_matrix_sync(scr_s, acc_s, BWD_SCR, wmma::mem_row_major);
-        wmma::store_matrix_sync(scr_d, acc_d, BWD_SCR, wmma::mem_row_major);
-        __syncwarp();
-        const int r = lane >> 1, c0 = (lane & 1) * 8;
-        const int i = ti * 16 + r;
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            const int j = tj * 16 + c0 + cc;
-            float pd_ = 0.f, ds = 0.f;
-            if (i < L && j < L) {
-                const float dist = fabsf((float)(s_pos[i] - s_pos[j]));
-                const float s = scr_s[r * BWD_SCR + c0 + cc] * p.sm_scale - coef * dist;
-                const float pr = __expf(s - s_lse[i]);
-                float ks = 1.f;
-                if (p.drop_p > 0.f) ks = attn_keep(p.seed, bh, L, i, j, p.drop_p) ? inv_keep : 0.f;
-                const float dp = scr_d[r * BWD_SCR + c0 + cc] * ks;
-                ds = pr * (dp - s_delta[i]);
-                pd_ = pr * ks;
-                dc_part -= ds * dist;
-            }
-            sPd[i * ldp + j] = __float2bfloat16_rn(pd_);
-            sdS[i * ldp + j] = __float2bfloat16_rn(ds);
-        }
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // ---- stage 2: dV = Pd^T dO, dK = dS^T Q * scale, dQ = dS K * scale
-    bf16* dqkv = reinterpret_cast<bf16*>(p.dqkv);
-    for (int tile = warp; tile < 3 * nt * 4; tile += 8) {
-        const int which = tile / (nt * 4);  // 0 dQ, 1 dK, 2 dV
-        const int rem = tile - which * nt * 4;
-        const int tr = rem >> 2, tc = rem & 3;
-        wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc;
-        wmma::fill_fragment(acc, 0.f);
-        for (int k = 0; k < LP; k += 16) {
-            wmma::fragment<wmma::matrix_b, 16, 16, 16, bf16, wmma::row_major> fb;
-            if (which == 0) {
-                wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::row_major> fa;
-                wmma::load_matrix_sync(fa, sdS + tr * 16 * ldp + k, ldp);
-                wmma::load_matrix_sync(fb, sK + k * BWD_LD + tc * 16, BWD_LD);
-                wmma::mma_sync(acc, fa, fb, acc);
-            } else {
-                wmma::fragment<wmma::matrix_a, 16, 16, 16, bf16, wmma::col_major> fa;
-                wmma::load_matrix_sync(fa, (which == 1 ? sdS : sPd) + k * ldp + tr * 16, ldp);
-                wmma::load_matrix_sync(fb, (which == 1 ? sQ : sdO) + k * BWD_LD + tc * 16, BWD_LD);
-                wmma::mma_sync(acc, fa, fb, acc);
-            }
-        }
-        wmma::store_matrix_sync(scr_s, acc, BWD_SCR, wmma::mem_row_major);
-        __syncwarp();
-        const int r = lane >> 1, c0 = (lane & 1) * 8;
-        const int i = tr * 16 + r;
-        if (i < L) {
-            const float sc = which == 2 ? 1.0f : p.sm_scale;
-            uint4 o;
-            o.x = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 0] * sc, scr_s[r * BWD_SCR + c0 + 1] * sc);
-            o.y = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 2] * sc, scr_s[r * BWD_SCR + c0 + 3] * sc);
-            o.z = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 4] * sc, scr_s[r * BWD_SCR + c0 + 5] * sc);
-            o.w = pack_bf16x2(scr_s[r * BWD_SCR + c0 + 6] * sc, scr_s[r * BWD_SCR + c0 + 7] * sc);
-            *reinterpret_cast<uint4*>(dqkv + ((long long)b * L + i) * 3 * D + which * D + h * HD + tc * 16 + c0) = o;
-        }
-        __syncwarp();
-    }
-
-    // ---- stage 3: d(alibi_scale)
-    dc_part = warp_sum(dc_part);
-    if (lane == 0) s_dc[warp] = dc_part;
-    __syncthreads();
-    if (tid == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr) {
-        float s = 0.f;
-        for (int w = 0; w < 8; ++w) s += s_dc[w];
-        if (p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
-            atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, s * p.slopes[h]);
-    }
-}
+constexpr int BWD_LMAX = 160;  // tokens per sequence the shared-memory-resident backward supports
 
 // ------------------------------------------------------------------------------------------
 // backward, tcgen05 (student shapes: L <= 160 kept tokens), persistent over (batch, head)
