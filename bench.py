@@ -26,6 +26,8 @@ if ROOT not in sys.path:
 
 FLOP_PER_CLIP = {"large": 6.12e12, "base": 2.29e12}  # SURVEY.md section 8(d), algorithmic, fwd+bwd+teacher
 METRIC = "pretrain 10s-clip samples/sec"
+WORKLOAD = ("animal2vec-{model} pretraining step (configs[2]), 10-s 8 kHz clips, M=12 clones, EMA teacher, mixup, dropout, "
+            "AdamW + clip + EMA update in the step")
 UNIT = "samples/s"
 
 
@@ -158,8 +160,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": warm, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"animal2vec-{args.model} pretraining step, 10-s 8 kHz clips, M=12 clones",
-                   "clips_per_step": 1},
+        "config": {"workload": WORKLOAD.format(model=args.model), "clips_per_step": 1,
+                   "sample": "one clip (12 clones) per step: forward + backward + EMA update, the unit SURVEY.md "
+                             "section 8(d) config 1 times on the CPU (no optimizer step, mixup off)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -289,8 +292,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"animal2vec-{args.model} pretraining step (configs[2]), 10-s 8 kHz clips, M=12 clones, "
-                               "EMA teacher, mixup, dropout, AdamW + clip + EMA update in the step",
+        "config": {"workload": WORKLOAD.format(model=args.model),
                    "clips_per_gpu_per_step": B, "global_batch": B * world, "samples_per_clip": n,
                    "parallelism": f"dp{world}", "l2_policy": "inputs and activations (>10 GB per step) exceed the 126 MB L2; "
                    "a different synthetic batch every step"},

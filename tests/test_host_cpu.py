@@ -258,3 +258,22 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
         assert ctypes.sizeof(cls) == int(size), (name, ctypes.sizeof(cls), size)
         py_offs = [getattr(cls, f).offset for f, _ in cls._fields_]
         assert py_offs == [int(o) for o in offs], (name, py_offs, offs, fields[name])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) on the tiny model: one JSON line with the
+    contract's keys, the same metric / unit / workload text as the B200 arm, and zero GPU launches."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny",
+                          "--steps", "1", "--warmup", "0"], check=True, capture_output=True, text=True, timeout=300).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    import bench
+
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
+    assert line["config"]["workload"] == bench.WORKLOAD.format(model="tiny")
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
