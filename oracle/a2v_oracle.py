@@ -529,6 +529,24 @@ def pretrain_forward(student: Dict[str, Tensor], teacher: Dict[str, Tensor], cfg
     return res
 
 
+def extract_features(student: Dict[str, Tensor], cfg: OracleConfig, source: Tensor) -> Dict[str, object]:
+    """Data2VecMultiModel.extract_features (data2vec2.py:1112-1123 -> forward(features_only=True, mask=False),
+    :632-728) in eval mode: the student on the unmasked full-length sequence. Returns the reference's dict
+    (``layer_results`` = FFN outputs of the main blocks, what the finetune head averages, wav2vec2.py:446-462).
+    First piece of the "next" row SURVEY.md section 8(f)-1; pinned by tests/golden/tiny_features.npz."""
+    lf = local_features(student, cfg, source)
+    b, t, _ = lf.shape
+    pos = torch.arange(t).unsqueeze(0).expand(b, -1)
+    bias = alibi_bias(cfg, student[ENC + "alibi_scale"], pos)
+    x = lf + positional_encoder(student, cfg, lf)
+    x = prenet(student, cfg, x, bias)
+    layer_results = []
+    for j in range(cfg.depth):
+        x, ffn = alt_block(student, f"blocks.{j}.", x, bias, cfg)
+        layer_results.append(ffn)
+    return {"x": x, "linear_eval_projection": None, "padding_mask": None, "layer_results": layer_results, "mask": None}
+
+
 def make_teacher(student: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """make_ema_teacher / make_target_model (data2vec2.py:345-384): fp32 copy of the shared keys."""
     return {k: v.detach().clone().float() for k, v in student.items() if is_teacher_key(k)}

@@ -120,3 +120,25 @@ def test_param_inventory_counts():
     teacher = sum(int(np.prod(s)) for k, s in shapes.items() if O.is_teacher_key(k))
     assert total == 315_830_026
     assert teacher == 308_542_480
+
+
+def test_oracle_extract_features_matches_reference_golden():
+    """The inference / finetune entry (features_only, unmasked, eval mode): oracle vs the reference's own output
+    (tests/golden/make_golden_features.py). Oracle-only this round: the pin a B200 implementation of SURVEY.md section
+    8(f)-1 will be checked against."""
+    g = _load("tiny_features.npz")
+    cfg = O.tiny_config()
+    params = O.init_params(cfg, 0)
+    n = int(g["n"])
+    x = F.layer_norm(torch.randn(int(g["b"]), n, generator=torch.Generator().manual_seed(int(g["seed_x"]))), (n,))
+    with torch.no_grad():
+        res = O.extract_features(params, cfg, x)
+    assert len(res["layer_results"]) == int(g["n_layers"])
+    assert _rel(res["x"][:, ::7, ::5], g["x"]) < 1e-5
+    assert abs(float(res["x"].double().norm()) - float(g["x_norm"])) < 1e-4 * float(g["x_norm"])
+    for i, l in enumerate(res["layer_results"]):
+        assert _rel(l[:, ::7, ::5], g[f"layer{i}"]) < 1e-5, i
+        assert abs(float(l.double().norm()) - float(g["layer_norms"][i])) < 1e-4 * float(g["layer_norms"][i])
+    k = cfg.average_top_k_layers
+    top = sum(res["layer_results"][-k:]) / len(res["layer_results"][-k:])
+    assert _rel(top[:, ::7, ::5], g["topk_mean"]) < 1e-5
