@@ -547,6 +547,46 @@ def extract_features(student: Dict[str, Tensor], cfg: OracleConfig, source: Tens
     return {"x": x, "linear_eval_projection": None, "padding_mask": None, "layer_results": layer_results, "mask": None}
 
 
+def finetune_logits(student: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, proj_w: Tensor, proj_b: Tensor,
+                    top_k: Optional[int] = None) -> Tensor:
+    """Wav2VecEncoderModOut.forward in eval mode (wav2vec2.py:437-482): extract_features, mean of the top-k FFN
+    outputs, final dropout (off), ``proj`` = Linear(D, classes). Returns (B, T, classes) logits."""
+    res = extract_features(student, cfg, source)
+    k = top_k or cfg.average_top_k_layers
+    lrs = res["layer_results"][-k:]
+    x = sum(lrs) / len(lrs)
+    return F.linear(x, proj_w, proj_b)
+
+
+def sigmoid_focal_loss(inputs: Tensor, targets: Tensor, alpha: float = 0.25, gamma: float = 2.0,
+                       reduction: str = "none") -> Tensor:
+    """nn/utils.py:971-1010 (RetinaNet focal loss on logits, fp32): BCE-with-logits * (1 - p_t)^gamma * alpha_t."""
+    x, t = inputs.float(), targets.float()
+    p = torch.sigmoid(x)
+    ce = F.binary_cross_entropy_with_logits(x, t, reduction="none")
+    p_t = p * t + (1 - p) * (1 - t)
+    loss = ce * (1 - p_t) ** gamma
+    if alpha >= 0:
+        loss = (alpha * t + (1 - alpha) * (1 - t)) * loss
+    if reduction == "mean":
+        return loss.mean()
+    if reduction == "sum":
+        return loss.sum()
+    return loss
+
+
+def confusion_counts(logits: Tensor, targets: Tensor, threshold: float) -> Tuple[int, int, int, int]:
+    """FinetuneCrossEntropyCriterion.compute_prec_rec_f1 (criterions.py:218-229) + confusion (utils.py:925-969),
+    multi-label branch: predictions = sigmoid(logits) >= threshold, micro-summed over classes -> (tp, fp, tn, fn)."""
+    pred = torch.sigmoid(logits.reshape(-1, logits.shape[-1]).float()) >= threshold
+    tru = targets.reshape(-1, targets.shape[-1]) > 0.5
+    tp = int((pred & tru).sum())
+    fp = int((pred & ~tru).sum())
+    tn = int((~pred & ~tru).sum())
+    fn = int((~pred & tru).sum())
+    return tp, fp, tn, fn
+
+
 def make_teacher(student: Dict[str, Tensor]) -> Dict[str, Tensor]:
     """make_ema_teacher / make_target_model (data2vec2.py:345-384): fp32 copy of the shared keys."""
     return {k: v.detach().clone().float() for k, v in student.items() if is_teacher_key(k)}

@@ -43,6 +43,25 @@ def main():
     # the finetune head's input (nn/wav2vec2.py:446-462): mean of the top-k FFN outputs
     k = cfg.average_top_k_layers
     out["topk_mean"] = G.sub(sum(lrs[-k:]) / len(lrs[-k:]))
+    # finetune head + criterion pieces (nn/wav2vec2.py:463-464 proj = nn.Linear(D, classes); nn/criterions.py:231-246 focal
+    # loss branch, :218-229 confusion counters) evaluated with the REFERENCE's own functions on seeded head weights / labels
+    from nn.utils import confusion, sigmoid_focal_loss  # the reference's implementations
+
+    classes = 12
+    gen = torch.Generator().manual_seed(9)
+    w = torch.randn(classes, cfg.embed_dim, generator=gen) * 0.2
+    bias = torch.randn(classes, generator=gen) * 0.1
+    top = sum(lrs[-k:]) / len(lrs[-k:])
+    logits = F.linear(top, w, bias)
+    target = (torch.rand(logits.shape, generator=gen) < 0.15).float()
+    loss_none = sigmoid_focal_loss(logits, target, reduction="none")
+    loss_sum = sigmoid_focal_loss(logits, target, reduction="sum")
+    thr = 0.5
+    preds = torch.where(torch.sigmoid(logits.view(-1, classes)) < thr, 0, 1)
+    tp, fp, tn, fn = confusion(preds, target.view(-1, classes).to(torch.int64))
+    out.update({"head_seed": np.int64(9), "classes": np.int64(classes), "logits": G.sub(logits, rows=7, cols=1),
+                "focal_none": G.sub(loss_none, rows=7, cols=1), "focal_sum": np.float64(loss_sum.double()),
+                "metric_threshold": np.float64(thr), "confusion": np.array([int(tp), int(fp), int(tn), int(fn)], dtype=np.int64)})
     path = os.path.join(HERE, "tiny_features.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, {k_: getattr(v, "shape", v) for k_, v in out.items()})

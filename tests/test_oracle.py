@@ -142,3 +142,23 @@ def test_oracle_extract_features_matches_reference_golden():
     k = cfg.average_top_k_layers
     top = sum(res["layer_results"][-k:]) / len(res["layer_results"][-k:])
     assert _rel(top[:, ::7, ::5], g["topk_mean"]) < 1e-5
+
+
+def test_oracle_finetune_head_focal_loss_and_confusion_match_reference():
+    """Finetune head (top-k mean -> Linear), sigmoid focal loss and the TP/FP/TN/FN counters against the reference's own
+    `sigmoid_focal_loss` / `confusion` run on the same seeded head weights and labels (make_golden_features.py)."""
+    g = _load("tiny_features.npz")
+    cfg = O.tiny_config()
+    params = O.init_params(cfg, 0)
+    n, classes = int(g["n"]), int(g["classes"])
+    x = F.layer_norm(torch.randn(int(g["b"]), n, generator=torch.Generator().manual_seed(int(g["seed_x"]))), (n,))
+    gen = torch.Generator().manual_seed(int(g["head_seed"]))
+    w = torch.randn(classes, cfg.embed_dim, generator=gen) * 0.2
+    bias = torch.randn(classes, generator=gen) * 0.1
+    with torch.no_grad():
+        logits = O.finetune_logits(params, cfg, x, w, bias)
+    target = (torch.rand(logits.shape, generator=gen) < 0.15).float()
+    assert _rel(logits[:, ::7], g["logits"]) < 1e-5
+    assert _rel(O.sigmoid_focal_loss(logits, target)[:, ::7], g["focal_none"]) < 1e-5
+    assert abs(float(O.sigmoid_focal_loss(logits, target, reduction="sum")) - float(g["focal_sum"])) < 1e-5 * float(g["focal_sum"])
+    assert list(O.confusion_counts(logits, target, float(g["metric_threshold"]))) == [int(v) for v in g["confusion"]]
