@@ -32,11 +32,21 @@ class ExpandedModelCriterionConfig:
     can_sum: bool = True
 
 
+_CriterionBase = registry.fairseq_bases()[1]  # fairseq's FairseqCriterion when importable, else torch.nn.Module
+
+
+def _init_base(obj, task) -> None:
+    if _CriterionBase is torch.nn.Module:
+        torch.nn.Module.__init__(obj)
+    else:
+        _CriterionBase.__init__(obj, task)
+    obj.task = task
+
+
 @registry.register_criterion("expanded_model", dataclass=ExpandedModelCriterionConfig)
-class ExpandedModelCriterion(torch.nn.Module):
+class ExpandedModelCriterion(_CriterionBase):
     def __init__(self, task, loss_weights=None, log_keys=None, can_sum=True):
-        super().__init__()
-        self.task = task
+        _init_base(self, task)
         self.loss_weights = loss_weights
         self.log_keys = log_keys
         self.can_sum_original = can_sum

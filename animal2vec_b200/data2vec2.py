@@ -13,6 +13,7 @@ sees ordinary ``nn.Parameter`` objects.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -20,7 +21,11 @@ import torch.nn as nn
 
 from . import registry
 from .config import Data2VecMultiConfig, Modality, from_dict, resolve
-from .engine import PretrainEngine, annealed_decay
+from .engine import ENC, PretrainEngine, annealed_decay
+
+# fairseq's BaseFairseqModel when fairseq is importable (then the class is also registered with fairseq under the
+# reference's name, see registry._register), torch.nn.Module otherwise
+_ModelBase = registry.fairseq_bases()[0]
 
 
 class _Holder(nn.Module):
@@ -50,11 +55,13 @@ class _StepFunction(torch.autograd.Function):
 
 
 @registry.register_model("data2vec_multi", dataclass=Data2VecMultiConfig)
-class Data2VecMultiModel(nn.Module):
+class Data2VecMultiModel(_ModelBase):
     def __init__(self, cfg: Data2VecMultiConfig, modalities=None, skip_ema=False, task=None, *,
-                 precision: str = "bf16", device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,
+                 precision: Optional[str] = None, device="cuda", init: Optional[Dict[str, torch.Tensor]] = None,
                  init_seed: int = 0):
         super().__init__()
+        if precision is None:  # build_model(cfg, task) has no precision argument: environment switch
+            precision = os.environ.get("A2V_PRECISION", "bf16")
         if isinstance(cfg, dict):
             cfg = from_dict(Data2VecMultiConfig, cfg)
         self.cfg = resolve(cfg)
@@ -68,6 +75,8 @@ class Data2VecMultiModel(nn.Module):
         self._params: Dict[str, nn.Parameter] = {}
         for name in self.engine.S.shapes:  # reference named_parameters() order
             p = nn.Parameter(self.engine.S.view(name), requires_grad=True)
+            if name.endswith("alibi_scale") and not self.cfg.modalities.audio.learned_alibi_scale:
+                p.requires_grad_(False)  # nn/modalities/base.py:134
             # nn/data2vec2.py:318-322
             if len(p.shape) == 1 or name.endswith(".bias") or "alibi_scale" in name or "p_swish" in name:
                 p.optim_overrides = {"optimizer": {"weight_decay_scale": 0}}
@@ -92,10 +101,42 @@ class Data2VecMultiModel(nn.Module):
         node.register_parameter(parts[-1], p)
 
     def _attach_grads(self) -> None:
+        """``p.grad`` are views of the engine's flat gradient buffer. An outer optimizer's ``zero_grad`` (fairseq's
+        FairseqOptimizer.zero_grad, torch's ``set_to_none=True`` default) only drops the views: whenever a view is
+        found missing its slice of the flat buffer is cleared before it is attached again, so gradients never pile
+        up across optimizer steps."""
+        missing = [n for n, p in self._params.items() if p.grad is None]
+        if missing:
+            if len(missing) == len(self._params):
+                self.engine.zero_grad()
+            else:
+                for n in missing:
+                    self.engine.S.gview(n).zero_()
         for name, p in self._params.items():
             g = self.engine.S.gview(name)
             if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                if p.grad is not None:  # a foreign gradient tensor was assigned: keep its values
+                    g.copy_(p.grad)
                 p.grad = g
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Clears the flat gradient buffer in one pass (the views stay attached regardless of ``set_to_none``)."""
+        self.engine.zero_grad()
+        self._attach_grads()
+
+    def _apply(self, fn, recurse=True):
+        """Parameters alias the engine's flat fp32 master buffer: ``.half()`` / ``.bfloat16()`` / ``.to(dtype)`` /
+        ``.cpu()`` would silently replace them with detached copies the kernels never read (fairseq calls
+        ``model.half()`` under ``common.fp16``). The arithmetic precision is chosen through ``precision=`` (bf16
+        kernels with fp32 masters); dtype or device moves are refused, same-device no-ops are accepted."""
+        probe = torch.empty(0, dtype=torch.float32, device=self.engine.device)
+        out = fn(probe)
+        if out.dtype != probe.dtype or out.device != probe.device:
+            raise RuntimeError(
+                "Data2VecMultiModel parameters are views of the CUDA engine's fp32 master buffer: casting or moving "
+                f"the module ({probe.dtype}/{probe.device} -> {out.dtype}/{out.device}) is not supported; choose "
+                "the compute precision with precision='bf16'|'fp32' at construction (no model.half())")
+        return self
 
     @classmethod
     def build_model(cls, cfg: Data2VecMultiConfig, task=None):
@@ -119,19 +160,43 @@ class Data2VecMultiModel(nn.Module):
 
     # ---------------------------------------------------------------------------------- checkpoint ABI
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
-        state = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
-        state[prefix + "_ema"] = {k: self.engine.E.view(k).detach().clone() for k in self.engine.E.names}
+        state = nn.Module.state_dict(self, *args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        if self.engine.has_teacher:
+            state[prefix + "_ema"] = {k: self.engine.E.view(k).detach().clone() for k in self.engine.E.names}
         return state
 
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+    def upgrade_state_dict_named(self, state_dict, name=""):
+        """nn/modalities/base.py:152-157: checkpoints written before ``alibi_scale`` gained its leading layer axis
+        hold a 4-D tensor. Applied to the student keys and to the ``_ema`` dict."""
+        pre = (name + ".") if name else ""
+        for sd in (state_dict, state_dict.get(pre + "_ema") if isinstance(state_dict.get(pre + "_ema"), dict) else None):
+            if sd is None:
+                continue
+            for k in (pre + ENC + "alibi_scale", ENC + "alibi_scale"):
+                if k in sd and torch.is_tensor(sd[k]) and sd[k].dim() == 4:
+                    sd[k] = sd[k].unsqueeze(0)
+        return state_dict
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False, model_cfg=None, args=None):
+        """nn/data2vec2.py:420-429 (``_ema`` consumed into the fp32 teacher shadow) + fairseq's
+        BaseFairseqModel.load_state_dict (upgrade hook first). Accepts the reference's checkpoint layouts: a plain
+        state dict, or the trainer's ``{"model": ..., "cfg": ...}`` file dict."""
+        if "model" in state_dict and isinstance(state_dict["model"], dict) and "_ema" not in state_dict:
+            state_dict = state_dict["model"]
         state_dict = dict(state_dict)
+        self.upgrade_state_dict_named(state_dict, "")
         ema = state_dict.pop("_ema", None)
-        out = super().load_state_dict(state_dict, strict=strict)
+        if self.engine.has_teacher and ema is None and strict:
+            raise KeyError("_ema")  # the reference asserts the key (nn/data2vec2.py:422-423)
+        if not self.engine.has_decoder:  # wav2vec2.py:332-335: decoder weights of a pretraining checkpoint are dropped
+            state_dict = {k: v for k, v in state_dict.items() if not k.startswith(ENC + "decoder.")}
+        out = nn.Module.load_state_dict(self, state_dict, strict=strict)
         self.engine.mark_student_updated()
-        if ema is not None:
-            self.engine.load_teacher(ema)
-        else:
-            self.engine.reset_teacher()
+        if self.engine.has_teacher:
+            if ema is not None:
+                self.engine.load_teacher(ema)
+            else:
+                self.engine.reset_teacher()
         return out
 
     # ---------------------------------------------------------------------------------- forward
@@ -141,15 +206,26 @@ class Data2VecMultiModel(nn.Module):
         ``AUDIO_regression`` entry is the already-summed loss as a 1-element fp32 tensor (the criterion's
         ``.float().sum()`` and ``backward()`` work unchanged; the unreduced (N_masked, D) tensor is never
         materialised)."""
-        if features_only or not mask:
-            raise NotImplementedError("features_only / mask=False (finetune + inference path) is a 'next' row of "
-                                      "SURVEY.md section 8(f); the pretraining path is implemented")
         if padding_mask is not None:
             raise NotImplementedError("padding_mask: the reference's own convert_padding_mask is broken "
                                       "(nn/modalities/audio.py:168); the shipped task disables padding")
         if mode is not None and (mode.name if isinstance(mode, Modality) else str(mode)) != "AUDIO":
             raise NotImplementedError("only the AUDIO modality exists on this path")
         cfg, e = self.cfg, self.engine
+        if features_only:
+            # nn/data2vec2.py:632-728 with features_only=True: clone_batch 1, masked rows stay in place
+            # (remove_masked = force_remove_masked, unsupported), no decoder, no teacher
+            if force_remove_masked:
+                raise NotImplementedError("force_remove_masked on the features_only path")
+            mask_np = None if precomputed_mask is None else precomputed_mask.detach().bool().cpu().numpy()
+            res = e.extract_features(source, ids=id, num_updates=self.num_updates, mask=bool(mask),
+                                     precomputed_mask=mask_np, training=self.training, need_grad=False)
+            return {"x": res["x"], "linear_eval_projection": None, "padding_mask": None,
+                    "layer_results": res["layer_results"], "mask": res["mask"]}
+        if not mask:
+            raise NotImplementedError("mask=False without features_only: the pretraining loss needs masked rows")
+        if not (e.has_teacher and e.has_decoder):
+            raise RuntimeError("remove_pretraining_modules() was called: only features_only=True forwards remain")
         self._check_guards()
         need_grad = torch.is_grad_enabled() and self.training
         mask_np = None
@@ -164,7 +240,16 @@ class Data2VecMultiModel(nn.Module):
         else:
             loss_t = loss_sum
         n = res["sample_size"]
-        pred_var, target_var = PretrainEngine.variances(res["colstats"], n)
+        stats = res["colstats"]
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size() > 1:
+            # compute_var (nn/data2vec2.py:1095-1105) all-reduces count, sum and sum of squares: one packed collective
+            packed = torch.cat([stats.reshape(-1), torch.tensor([float(n)], device=stats.device, dtype=stats.dtype)])
+            torch.distributed.all_reduce(packed)
+            stats, n_var = packed[:-1].view_as(stats), packed[-1]
+        else:
+            n_var = n
+        pred_var, target_var = PretrainEngine.variances(stats, n_var)
         result = {
             "losses": {"AUDIO_regression": loss_t},
             "sample_size": torch.tensor(n, dtype=torch.long, device=e.device),
@@ -194,4 +279,33 @@ class Data2VecMultiModel(nn.Module):
                             remove_extra_tokens=remove_extra_tokens)
 
     def remove_pretraining_modules(self, modality=None, keep_decoder=False):
-        raise NotImplementedError("finetune hand-over is a 'next' row (SURVEY.md section 8f-1)")
+        """nn/data2vec2.py:1125-1142: drop the EMA teacher, set clone_batch 1 and (unless ``keep_decoder``) the
+        decoder. Afterwards only ``features_only=True`` forwards (extract_features) are possible and the state
+        dict carries neither ``_ema`` nor decoder keys."""
+        if modality is not None and str(modality).lower() != "audio":
+            raise NotImplementedError("only the AUDIO modality exists on this path")
+        self.engine.drop_teacher()
+        self.cfg.clone_batch = 1
+        if not keep_decoder and self.engine.has_decoder:
+            self.engine.drop_decoder()
+            enc = self.modality_encoders.AUDIO
+            if "decoder" in enc._modules:
+                del enc._modules["decoder"]
+            for n in [n for n in self._params if n.startswith(ENC + "decoder.")]:
+                del self._params[n]
+
+    # ---------------------------------------------------------------------------------- fairseq model protocol
+    def prepare_for_inference_(self, cfg=None):
+        self.eval()
+
+    def max_positions(self):
+        return None
+
+    def get_targets(self, sample, net_output):
+        return sample.get("target") if isinstance(sample, dict) else None
+
+    def get_logits(self, net_output, reshape=True):
+        y = net_output["linear_eval_projection"]
+        if y is None:
+            raise NotImplementedError("with_labels (linear-eval projection during pretraining) is not on this path")
+        return y.reshape(-1, y.size(-1)) if reshape else y

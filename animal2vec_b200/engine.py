@@ -133,6 +133,8 @@ class PretrainEngine:
         self._build_packs()
         self.ctx = None
         self.kernel_launches = 0
+        self.has_teacher = True
+        self.has_decoder = True
 
     # ------------------------------------------------------------------------------------ support matrix
     @staticmethod
@@ -161,6 +163,7 @@ class PretrainEngine:
         if a.num_extra_tokens: bad.append("num_extra_tokens>0")
         if a.inverse_mask or a.mask_channel_prob or a.keep_masked_pct or a.remove_masks or a.mask_prob_min is not None:
             bad.append("mask variant")
+        if a.mask_length == 1: bad.append("mask_length=1 (random_masking branch, base.py:394-395)")
         if not a.encoder_zero_mask: bad.append("encoder_zero_mask=False")
         if a.ema_local_encoder: bad.append("ema_local_encoder")
         if a.local_grad_mult != 1.0: bad.append("local_grad_mult != 1")
@@ -193,6 +196,19 @@ class PretrainEngine:
             self.E.view(k).copy_(tensors[k].to(self.device, torch.float32).reshape(self.E.shapes[k]))
         self._teacher_dirty = True
         self._t16_valid = False
+
+    def drop_teacher(self) -> None:
+        """remove_pretraining_modules (nn/data2vec2.py:1125-1127): the EMA teacher and its fp32 shadow are released."""
+        self.has_teacher = False
+        self.E.data = self.E.data[:0]
+        self.T16 = self.T16[:0]
+        self.WT = _Weights()
+        self._pack_table_t = None
+
+    def drop_decoder(self) -> None:
+        """remove_pretraining_modules(keep_decoder=False): the decoder parameters stay in the flat buffer (unused,
+        zero gradient) but leave the state dict; pretraining forwards are refused from here on."""
+        self.has_decoder = False
 
     def mark_student_updated(self, s16_valid: bool = False) -> None:
         """The fp32 masters changed (optimizer step / state-dict load). ``s16_valid``: the bf16 flat copy was
@@ -310,12 +326,8 @@ class PretrainEngine:
         self._student_dirty = False
 
     def _alibi_of(self, F: P.FlatParams, W: _Weights) -> torch.Tensor:
-        if self.a.learned_alibi_scale:
-            return F.view(ENC + "alibi_scale").view(-1)
-        t = getattr(self, "_const_alibi", None)
-        if t is None:
-            t = self._const_alibi = torch.full((1,), float(self.a.alibi_scale), device=self.device)
-        return t
+        # the parameter always exists (base.py:116-134); learned_alibi_scale only decides whether it gets a gradient
+        return F.view(ENC + "alibi_scale").view(-1)
 
     def _refresh_teacher(self) -> None:
         if not self._teacher_dirty:
@@ -523,6 +535,8 @@ class PretrainEngine:
         and keeps what the backward needs in ``self.ctx``."""
         cfg, d, M = self.cfg, self.D, self.M
         L.require_device(source)
+        if not (self.has_teacher and self.has_decoder):
+            raise RuntimeError("pretraining forward after remove_pretraining_modules()")
         self._refresh_student()
         self._refresh_teacher()
         self.step_counter += 1
@@ -600,6 +614,30 @@ class PretrainEngine:
         self.ctx = c if save else None
         return {"loss_sum": loss_sum, "colstats": stats, "sample_size": n_masked, "masked_pct": 1.0 - tk / T,
                 "mask": mask, "T": T, "tk": tk}
+
+    # ------------------------------------------------------------------------------------ features_only path
+    def extract_features(self, source: torch.Tensor, ids=None, num_updates: int = 0, *, mask: bool = False,
+                         precomputed_mask: Optional[np.ndarray] = None, training: bool = False,
+                         need_grad: bool = False) -> Dict[str, object]:
+        """Data2VecMultiModel.forward(features_only=True) (nn/data2vec2.py:632-728; extract_features :1112-1123):
+        the STUDENT on the full-length sequence, clone_batch 1, masked rows kept in place. Returns ``x`` (B, T, D),
+        ``layer_results`` (FFN outputs of the main blocks, what the finetune head averages, nn/wav2vec2.py:446-462)
+        and the mask. Unmasked eval mode is the README inference contract (README.md:69-121)."""
+        L.require_device(source)
+        if mask or training or need_grad:
+            raise NotImplementedError("features_only with masking / training mode / gradients: use FinetuneEngine")
+        self._refresh_student()
+        d = self.D
+        x = source.to(torch.float32).contiguous()
+        B = x.shape[0]
+        lf = self._fe_forward(x, SimpleNamespace(), False)
+        T = lf.shape[1]
+        x_pos = self._posconv_forward(self.WS, lf, None)
+        xs = self._add(x_pos.view(B * T, d), lf.view(B * T, d))
+        del x_pos
+        layer_results: List[torch.Tensor] = []
+        xs = self._encoder_forward(self.WS, xs, B, T, None, False, None, layer_results, None)
+        return {"x": xs.view(B, T, d), "layer_results": layer_results, "mask": None, "local_features": lf}
 
     def _mask_static(self, B: int, T: int) -> dict:
         return dict(seed=self.cfg.seed, batch=B, frames=T, clone_batch=self.M, mask_prob=self.a.mask_prob,
@@ -796,7 +834,7 @@ class PretrainEngine:
         """set_num_updates (nn/data2vec2.py:386-410): anneal the decay, then fairseq EMAModule.step on the
         shared parameters (fp32 shadow) and refresh the teacher's bf16 copy -- one fused launch."""
         decay = annealed_decay(self.cfg, num_updates)
-        if decay < 1:
+        if decay < 1 and self.has_teacher:
             n = self.E.total
             ops.ema_step(self.S.data[:n], self.E.data, None if self.fp32 else self.T16, decay)
             self._teacher_dirty = True

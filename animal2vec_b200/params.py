@@ -48,7 +48,8 @@ def student_param_shapes(cfg: Data2VecMultiConfig) -> Dict[str, Tuple[int, ...]]
     d, hidden = cfg.embed_dim, int(cfg.embed_dim * cfg.mlp_ratio)
     layers = parse_conv_layers(a.conv_feature_layers)
     s: Dict[str, Tuple[int, ...]] = {}
-    s[ENC + "alibi_scale"] = (1, 1, a.num_alibi_heads, 1, 1)
+    # nn/modalities/base.py:116-134 (learned_alibi_scale_per_layer is refused by the engine)
+    s[ENC + "alibi_scale"] = (1, 1, a.num_alibi_heads if a.learned_alibi_scale_per_head else 1, 1, 1)
     c0, _k0, _ = layers[0]
     le = ENC + "local_encoder.conv_layers."
     s[le + "0.0.low_hz_"] = (c0, 1)

@@ -1,29 +1,48 @@
 """Name registries mirroring fairseq's ``@register_model / @register_task / @register_criterion``.
 
-The reference registers its classes with fairseq (nn/data2vec2.py:168, nn/audio_tasks.py:92,
-nn/criterions.py:388). fairseq is not a dependency of this package; when it IS importable the same
-classes are additionally registered with it under the same names, so a fairseq/hydra config that names
-``data2vec_multi`` / ``expanded_model`` resolves to the B200 implementations.
+The reference registers its classes with fairseq (nn/data2vec2.py:168, nn/wav2vec2.py:57,
+nn/audio_tasks.py:92, nn/criterions.py:137,388). fairseq is not a dependency of this package. When it IS
+importable, the classes below derive from fairseq's own base classes (:func:`fairseq_bases`) and are
+registered with fairseq's registrars under the same names, so a fairseq/hydra config that names
+``data2vec_multi`` / ``expanded_model`` / ``audio_ccas`` resolves to the B200 implementations. A registrar
+error (duplicate name, wrong base class) is raised, never swallowed. The fairseq side of this hook is
+exercised against a stub package in tests/test_host_cpu.py (fairseq itself cannot be installed here).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict
+import importlib
+from typing import Callable, Dict, Tuple
 
 MODELS: Dict[str, type] = {}
 CRITERIA: Dict[str, type] = {}
 TASKS: Dict[str, type] = {}
 DATACLASSES: Dict[str, type] = {}
+FAIRSEQ_REGISTERED: Dict[str, str] = {}  # "<kind>:<name>" -> class name, filled when fairseq took the class
+
+_KIND_MODULE = {"model": ("fairseq.models", "register_model"),
+                "criterion": ("fairseq.criterions", "register_criterion"),
+                "task": ("fairseq.tasks", "register_task")}
 
 
-def _also_fairseq(kind: str, name: str, dataclass):
-    try:  # pragma: no cover - fairseq is absent in the build image
-        import fairseq  # noqa: F401
-        from fairseq import criterions, models, tasks
+def fairseq_available() -> bool:
+    try:
+        importlib.import_module("fairseq")
+        return True
+    except ImportError:
+        return False
 
-        return {"model": models.register_model, "criterion": criterions.register_criterion,
-                "task": tasks.register_task}[kind](name, dataclass=dataclass)
-    except Exception:
-        return None
+
+def fairseq_bases() -> Tuple[type, type, type]:
+    """(model base, criterion base, task base): fairseq's when importable, else torch.nn.Module / object."""
+    import torch.nn as nn
+
+    if not fairseq_available():
+        return nn.Module, nn.Module, object
+    from fairseq.criterions import FairseqCriterion
+    from fairseq.models import BaseFairseqModel
+    from fairseq.tasks import FairseqTask
+
+    return BaseFairseqModel, FairseqCriterion, FairseqTask
 
 
 def _register(table: Dict[str, type], kind: str, name: str, dataclass) -> Callable[[type], type]:
@@ -34,6 +53,11 @@ def _register(table: Dict[str, type], kind: str, name: str, dataclass) -> Callab
         if dataclass is not None:
             DATACLASSES[name] = dataclass
         cls._registry_name = name
+        if fairseq_available():
+            mod_name, fn_name = _KIND_MODULE[kind]
+            registrar = getattr(importlib.import_module(mod_name), fn_name)
+            registrar(name, dataclass=dataclass)(cls)  # raises on a duplicate name / wrong base class
+            FAIRSEQ_REGISTERED[f"{kind}:{name}"] = cls.__name__
         return cls
 
     return deco

@@ -128,14 +128,16 @@ class PretrainTrainer:
         lo, hi = self.block_ranges[j]
         self.reducer.reduce_range(lo, hi)
 
-    def train_step(self, micro_batches: Sequence[Tuple[torch.Tensor, Optional[Sequence[int]]]],
-                   sync_log: bool = False) -> Dict[str, object]:
-        """One optimizer update from ``len(micro_batches)`` accumulated micro-batches (``update_freq``)."""
-        e, o = self.e, self.o
+    def accumulate_and_reduce(self, micro_batches: Sequence[Tuple[torch.Tensor, Optional[Sequence[int]]]]):
+        """Forward + backward of every micro-batch into the flat gradient buffer, bucketed SUM all-reduce of the
+        gradients (overlapped with the last backward) and ONE packed all-reduce of the step statistics
+        [loss sum, sample size, 4 x D column sums]. Afterwards every rank holds the global sums."""
+        e = self.e
         e.zero_grad()
         self.stats.zero_()
         n_mb = len(micro_batches)
         sample_size = 0
+        res = None
         for i, (source, ids) in enumerate(micro_batches):
             res = e.forward(source, ids, self.num_updates, training=True)
             last = i == n_mb - 1
@@ -149,6 +151,13 @@ class PretrainTrainer:
         if self.reducer.enabled:
             dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=self.group)  # C1 + C3 packed
         self.reducer.finish()
+        return res
+
+    def train_step(self, micro_batches: Sequence[Tuple[torch.Tensor, Optional[Sequence[int]]]],
+                   sync_log: bool = False) -> Dict[str, object]:
+        """One optimizer update from ``len(micro_batches)`` accumulated micro-batches (``update_freq``)."""
+        e, o = self.e, self.o
+        res = self.accumulate_and_reduce(micro_batches)
         # grads *= 1/sum(sample_size); clip to clip_norm; Adam; EMA
         self.sumsq.zero_()
         ops.sumsq(e.S.grad, self.sumsq)

@@ -1,0 +1,188 @@
+"""GPU parity of the randomised sub-paths the benchmarked configuration runs ("parity holes"):
+
+* attention dropout, forward AND backward, against fp32 torch autograd driven by the kernel's OWN keep mask
+  (the mask depends only on (seed, batch*head, L, i, j); it is read back through the kernel's linearity in V);
+* the decoder-input dropout pairing: forward keys the keep flags by SOURCE row, backward by DESTINATION row
+  (nn/modalities/base.py:162-192 -> engine.forward / engine.backward) -- must equal autograd of scatter(drop(x));
+* full-size (animal2vec-large, one 10-s clip, 12 clones) bf16 gradients against the CPU oracle for named tensors.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import a2v_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def _recover_attention_keep(batch, seq, heads, drop_p, seed, pos):
+    """keep[b, h, i, j] of a2v_attn_fwd: with q = k = 0 and no ALiBi the probabilities are uniform, so
+    out[b, i, h, d] = sum_j keep[i, j] / ((1 - p) L) * V[j, h, d]; one-hot V blocks of 64 keys read the mask out."""
+    from animal2vec_b200 import ops
+
+    d = heads * 64
+    keep = torch.zeros(batch, heads, seq, seq, device="cuda", dtype=torch.bool)
+    for c0 in range(0, seq, 64):
+        qkv = torch.zeros(batch, seq, 3 * d, device="cuda", dtype=torch.bfloat16)
+        n = min(64, seq - c0)
+        eye = torch.eye(64, device="cuda", dtype=torch.bfloat16)[:n]  # key c0 + r -> unit vector r
+        qkv[:, c0:c0 + n, 2 * d:] = eye.repeat(1, heads)
+        out, _ = ops.attn_fwd(qkv, batch, seq, heads, pos=pos, drop_p=drop_p, seed=seed)
+        o = out.float().view(batch, seq, heads, 64).permute(0, 2, 1, 3)  # (b, h, i, 64)
+        keep[:, :, :, c0:c0 + n] = o[..., :n] > 0.5 / seq
+    return keep
+
+
+@pytest.mark.parametrize("seq,with_pos", [(129, False), (148, True), (97, True)])
+def test_attention_dropout_forward_and_backward_match_autograd_with_the_kernels_mask(seq, with_pos):
+    from animal2vec_b200 import ops
+
+    batch, heads, drop_p, seed = 3, 4, 0.1, 0x5EEDF00D12345
+    d = heads * 64
+    pos = None
+    if with_pos:
+        pos = torch.stack([torch.randperm(2000, device="cuda", generator=_g(10 + i))[:seq].sort().values
+                           for i in range(batch)]).to(torch.int32).contiguous()
+    keep = _recover_attention_keep(batch, seq, heads, drop_p, seed, pos)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - drop_p)) < 0.01, frac
+    # the mask must not depend on the data: a second read-out through different V blocks is identical
+    assert torch.equal(keep, _recover_attention_keep(batch, seq, heads, drop_p, seed, pos))
+
+    qkv = torch.randn(batch, seq, 3 * d, device="cuda", generator=_g(1)).bfloat16()
+    slopes = torch.tensor([2.0 ** (-0.5 * (h + 1)) for h in range(heads)], device="cuda")
+    scale = torch.rand(heads, device="cuda", generator=_g(2)) + 0.5
+    dout = torch.randn(batch, seq, d, device="cuda", generator=_g(3)).bfloat16()
+
+    qr = qkv.float().clone().requires_grad_(True)
+    sr = scale.clone().requires_grad_(True)
+    q, k, v = qr.view(batch, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q * 64 ** -0.5) @ k.transpose(-1, -2)
+    p_ = pos.float() if pos is not None else torch.arange(seq, device="cuda").float().expand(batch, seq)
+    dist = (p_[:, :, None] - p_[:, None, :]).abs()
+    s = s - (slopes * sr.clamp_min(0)).view(1, heads, 1, 1) * dist[:, None]
+    a = s.softmax(-1) * keep.float() / (1 - drop_p)  # modules.py:399-401: softmax, then dropout
+    ref = (a @ v).transpose(1, 2).reshape(batch, seq, d)
+    ref.backward(dout.float())
+
+    out, lse = ops.attn_fwd(qkv, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=drop_p, seed=seed)
+    assert _rel(out, ref) < 1e-2, _rel(out, ref)
+    dsc = torch.zeros(heads, device="cuda")
+    dqkv = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale,
+                        dalibi_scale=dsc, drop_p=drop_p, seed=seed)
+    assert _rel(dqkv, qr.grad) < 2e-2, _rel(dqkv, qr.grad)
+    assert _rel(dsc, sr.grad) < 2e-2, (dsc, sr.grad)
+    # a different seed gives a different mask (and so a different gradient)
+    dq2 = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale,
+                       drop_p=drop_p, seed=seed + 1)
+    assert _rel(dq2, qr.grad) > 5e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_decoder_input_dropout_forward_backward_pairing(dtype):
+    """decoder_input (base.py:162-192): x = dropout(x); cat mask tokens; gather(ids_restore). The engine's forward
+    is row_gather(xs, restore_src, drop_by_src=True) and its backward row_gather(dx, keep_src_clone) with the same
+    seed keyed by destination row: together they must be the autograd pair of scatter(dropout(x))."""
+    from animal2vec_b200 import ops
+
+    b, m, t, d, tk, p, seed = 2, 3, 200, 128, 31, 0.1, 0xABCDEF0123
+    rows = b * m
+    mask = torch.ones(rows, t, dtype=torch.uint8)
+    g = torch.Generator().manual_seed(0)
+    for r in range(rows):
+        mask[r, torch.randperm(t, generator=g)[:tk]] = 0
+    mask = mask.cuda()
+    mi = ops.mask_index(mask, tk, m)
+    keep_idx = torch.stack([torch.nonzero(mask[r] == 0).flatten() for r in range(rows)])  # (rows, tk)
+
+    ones = torch.ones(rows * tk, d, device="cuda", dtype=dtype)
+    probe = ops.row_gather(ones, mi.restore_src, rows * t, drop_p=p, drop_seed=seed, drop_by_src=True,
+                           out_shape=(rows, t, d))
+    kept_rows = torch.gather(probe, 1, keep_idx.unsqueeze(-1).expand(-1, -1, d)).float()  # (rows, tk, d)
+    keep = kept_rows > 0.5
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    assert torch.all((kept_rows == 0) | ((kept_rows - 1 / (1 - p)).abs() < 1e-2))
+    assert torch.all(probe[mask.bool()] == 0)  # mask tokens (noise std 0 here) are never dropped-in
+
+    xs = torch.randn(rows * tk, d, device="cuda", generator=_g(1)).to(dtype)
+    w = torch.randn(rows, t, d, device="cuda", generator=_g(2)).to(dtype)
+    xr = xs.float().clone().requires_grad_(True)
+    dropped = xr.view(rows, tk, d) * keep.float() / (1 - p)
+    ref = torch.zeros(rows, t, d, device="cuda").scatter(1, keep_idx.unsqueeze(-1).expand(-1, -1, d), dropped)
+    (ref * w.float()).sum().backward()
+
+    fwd = ops.row_gather(xs, mi.restore_src, rows * t, drop_p=p, drop_seed=seed, drop_by_src=True, out_shape=(rows, t, d))
+    tol = 1e-6 if dtype == torch.float32 else 4e-3
+    assert _rel(fwd, ref) < tol, _rel(fwd, ref)
+    bwd = ops.row_gather(w.view(rows * t, d), mi.keep_src_clone, rows * tk, drop_p=p, drop_seed=seed,
+                         out_shape=(rows * tk, d))
+    assert _rel(bwd, xr.grad) < tol, _rel(bwd, xr.grad)
+    # the wrong pairing (both keyed by source row) must NOT pass: guards the test itself
+    wrong = ops.row_gather(w.view(rows * t, d), mi.keep_src_clone, rows * tk, drop_p=p, drop_seed=seed,
+                           drop_by_src=True, out_shape=(rows * tk, d))
+    assert _rel(wrong, xr.grad) > 0.1
+
+
+LARGE_GRAD_KEYS = [
+    "blocks.0.attn.qkv.weight", "blocks.0.mlp.fc1.weight", "blocks.15.attn.qkv.weight", "blocks.15.mlp.fc1.weight",
+    "blocks.15.mlp.fc2.bias", "blocks.7.attn.proj.weight", "blocks.7.norm2.weight",
+    O.ENC + "context_encoder.blocks.0.attn.qkv.weight", O.ENC + "context_encoder.blocks.7.mlp.fc2.weight",
+    O.ENC + "context_encoder.norm.weight", O.ENC + "alibi_scale",
+    O.ENC + "relative_positional_encoder.1.0.weight", O.ENC + "relative_positional_encoder.5.0.weight",
+    O.ENC + "relative_positional_encoder.5.0.bias",
+    O.ENC + "decoder.blocks.0.0.weight", O.ENC + "decoder.blocks.3.0.weight", O.ENC + "decoder.proj.weight",
+    O.ENC + "project_features.2.weight", O.ENC + "local_encoder.conv_layers.1.0.weight",
+    O.ENC + "local_encoder.conv_layers.4.0.weight", O.ENC + "local_encoder.conv_layers.7.0.weight",
+    O.ENC + "local_encoder.conv_layers.0.0.low_hz_", O.ENC + "local_encoder.conv_layers.0.0.band_hz_",
+    O.ENC + "local_encoder.conv_layers.0.2.1.weight",
+]
+
+
+def test_large_config_bf16_gradients_match_the_cpu_oracle():
+    """The headline configuration at full size, one clip: every named gradient of the bf16 backward within 3e-2
+    relative (L2) of the CPU oracle's fp32 autograd on the same weights, input, ids and (bit-exact) masks."""
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200.engine import PretrainEngine
+
+    ocfg = O.large_config()
+    params = O.init_params(ocfg, 0)
+    n = 80000
+    x = F.layer_norm(torch.randn(1, n, generator=torch.Generator().manual_seed(3)), (n,))
+    ids = torch.arange(1) + 11
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    student = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    teacher = O.make_teacher(params)
+    ores = O.pretrain_forward(student, teacher, ocfg, x, ids, 2)
+    oloss = ores["losses"]["AUDIO_regression"].sum()
+    oloss.backward()
+
+    eng = PretrainEngine(Cfg.no_randomness(Cfg.shipped_large()), "cuda", precision="bf16", init=params)
+    eng.zero_grad()
+    res = eng.forward(x.cuda(), ids, 2)
+    assert np.array_equal(res["mask"], ores["mask"].numpy())
+    loss = float(res["loss_sum"].item())
+    assert abs(loss - float(oloss)) / abs(float(oloss)) < 1e-2
+    eng.backward()
+    worst = {}
+    for k in LARGE_GRAD_KEYS:
+        got, want = eng.S.gview(k).float().cpu(), student[k].grad
+        assert float(want.norm()) > 0, k
+        worst[k] = _rel(got, want)
+    bad = {k: v for k, v in worst.items() if not v < 3e-2}
+    assert not bad, (bad, worst)
+    # whole flat gradient: cosine with the oracle's
+    flat_o = torch.cat([student[k].grad.reshape(-1) for k in eng.S.names]).double()
+    flat_g = torch.cat([eng.S.gview(k).reshape(-1).double().cpu() for k in eng.S.names])
+    cos = float((flat_o * flat_g).sum() / (flat_o.norm() * flat_g.norm()))
+    assert cos > 0.9995, cos
