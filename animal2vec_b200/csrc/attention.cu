@@ -16,64 +16,9 @@
 //                             in shared memory, all five products on tcgen05 with TMEM accumulators.
 //   attn_qk_bound_kernel    : max |q|, max |k| per head (the data-dependent part of the ALiBi key-tile window).
 //   attn_*_ref_kernel       : fp32 CUDA-core kernels for the fp32 validation mode.
-#include "common.cuh"
-#include "../../include/a2v_capi.h"
+#include "attention_common.cuh"
 
 namespace a2v {
-
-constexpr int HD = 64;
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-
-struct AttnParams {
-    const void* qkv;
-    void* out;
-    float* lse;
-    const int* pos;
-    const float* slopes;
-    const float* alibi_scale;
-    int alibi_scale_stride;
-    int batch, L, H, D;
-    float sm_scale;
-    float drop_p;
-    unsigned long long seed;
-    const void* dout;
-    void* dqkv;
-    float* dalibi_scale;
-    const float* qk_bound;  // optional, (batch * H) x {max |q|^2, max |k|^2} of the head (see attn_qk_bound_kernel)
-};
-
-__device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
-    float sc = 1.0f;
-    if (p.alibi_scale != nullptr) sc = fmaxf(p.alibi_scale[h * p.alibi_scale_stride], 0.f);
-    return p.slopes != nullptr ? p.slopes[h] * sc : 0.f;
-}
-
-// Attention-dropout bits: 16 bits per (query row, key), generated four keys at a time from 32-bit
-// multiply-xorshift hashes of a per-row key (one hash pair per group of 4 keys, ~3.5 instructions per
-// probability). Every kernel of this file (forward, both backwards, fp32 validation) derives its keep
-// flags from these two functions, so forward and backward always agree.
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-    return x;
-}
-__device__ __forceinline__ uint32_t attn_row_key(unsigned long long seed, long long bh, int L, int i) {
-    return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + (uint32_t)(bh * L + i)));
-}
-// .x: keys 4g, 4g+1 (low / high half), .y: keys 4g+2, 4g+3
-__device__ __forceinline__ uint2 attn_bits4(uint32_t row_key, int g) {
-    uint32_t a = row_key + (uint32_t)g * 0x9E3779B9U;
-    uint32_t b = a + 0x85ebca6bU;
-    a *= 0x7feb352dU; a ^= a >> 15; a *= 0x846ca68bU; a ^= a >> 16;
-    b *= 0x7feb352dU; b ^= b >> 15; b *= 0x846ca68bU; b ^= b >> 16;
-    return make_uint2(a, b);
-}
-__device__ __forceinline__ uint32_t attn_drop_threshold(float pd) { return (uint32_t)(pd * 65536.0f); }
-__device__ __forceinline__ bool attn_keep(unsigned long long seed, long long bh, int L, int i, int j, float pd) {
-    const uint2 bits = attn_bits4(attn_row_key(seed, bh, L, i), j >> 2);
-    const uint32_t w = (j & 2) ? bits.y : bits.x;
-    return ((w >> (16 * (j & 1))) & 0xffffu) >= attn_drop_threshold(pd);
-}
 
 // ------------------------------------------------------------------------------------------
 // forward, tcgen05
@@ -92,11 +37,6 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximu
 // fp32 softmax, nn/modalities/modules.py:396-399, rounds such terms away as well).
 constexpr float ATT_SKIP_LOG2 = 50.0f;
 
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -952,7 +892,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             // d(alibi_scale[h]) += slope_h * sum(-dS * dist)  (only where the clamped scale is active)
             dc_part = warp_sum(dc_part);
             if (lane == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr &&
-                p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
+                p.alibi_scale[h * p.alibi_scale_stride] >= 0.f)
                 atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, dc_part * p.slopes[h]);
         }
     }
@@ -1069,16 +1009,44 @@ __global__ void __launch_bounds__(128) attn_bwd_ref_kernel(const AttnParams p) {
     __syncthreads();
     if (threadIdx.x == 0 && p.dalibi_scale != nullptr && p.alibi_scale != nullptr && p.slopes != nullptr) {
         const float s = s_dc[0] + s_dc[1] + s_dc[2] + s_dc[3];
-        if (p.alibi_scale[h * p.alibi_scale_stride] > 0.f)
+        if (p.alibi_scale[h * p.alibi_scale_stride] >= 0.f)
             atomicAdd(p.dalibi_scale + h * p.alibi_scale_stride, s * p.slopes[h]);
     }
 }
 
-typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn2 attn_tensor_map_encoder() {
+    static EncodeTiledFn2 encode = nullptr;  // idempotent initialisation: a race only repeats the lookup
+    if (encode == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym)
+            return nullptr;
+        encode = reinterpret_cast<EncodeTiledFn2>(sym);
+    }
+    return encode;
+}
 
-static int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
+int attn_make_map(CUtensorMap* out, const void* base, int cols, int L, int batch, int box_rows) {
+    EncodeTiledFn2 encode = attn_tensor_map_encoder();
+    if (encode == nullptr) {
+        a2v_set_error("attention: cuTensorMapEncodeTiled not available");
+        return A2V_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)L * cols * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        a2v_set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return A2V_ERR_CUDA;
+    }
+    return A2V_OK;
+}
+
+int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
     A2V_REQUIRE(d != nullptr, "attention: NULL descriptor");
     A2V_REQUIRE(d->dtype == A2V_F32 || d->dtype == A2V_BF16, "attention: bad dtype");
     A2V_REQUIRE(d->qkv && d->out, "attention: NULL qkv/out");
@@ -1092,6 +1060,8 @@ static int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
     p.sm_scale = d->sm_scale; p.drop_p = d->drop_p; p.seed = d->seed;
     p.dout = d->dout; p.dqkv = d->dqkv; p.dalibi_scale = d->dalibi_scale;
     p.qk_bound = d->qk_bound;
+    p.delta = nullptr;
+    p.dq_acc = nullptr;
     return A2V_OK;
 }
 
@@ -1193,8 +1163,22 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         attn_bwd_ref_kernel<<<grid, 128, 0, st>>>(p);
         return a2v_check_launch("attn_bwd_ref");
     }
+    A2V_REQUIRE(d->bwd_algo >= 0 && d->bwd_algo <= 2, "attention backward: bwd_algo must be 0 (auto), 1 (resident) or 2 (tiled)");
+    if (d->bwd_algo == 2 || (d->bwd_algo == 0 && p.L > BWD_LMAX)) {
+        // any length: key tiles resident, query tiles streamed (attention_bwd.cu); needs the prepared workspace
+        A2V_REQUIRE(d->workspace != nullptr &&
+                        (size_t)d->workspace_bytes >= a2v_attn_bwd_workspace_bytes(p.batch, p.L, p.H),
+                    "attention backward (bf16, tiled): workspace of a2v_attn_bwd_workspace_bytes() bytes required");
+        A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dout) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(d->workspace) & 15) == 0,
+                    "attention backward: qkv / dout / workspace not 16-byte aligned");
+        const size_t rows = (size_t)p.batch * (size_t)p.L;
+        p.delta = reinterpret_cast<const float*>(d->workspace);
+        p.dq_acc = reinterpret_cast<float*>(d->workspace) + ((rows * (size_t)p.H + 3) & ~(size_t)3);
+        return attn_bwd_tiled_launch(p, st);
+    }
     A2V_REQUIRE(p.L <= BWD_LMAX,
-                "attention backward (bf16): the shared-memory-resident kernels support at most %d tokens per "
+                "attention backward (bf16): the shared-memory-resident kernel supports at most %d tokens per "
                 "sequence, got %d", BWD_LMAX, p.L);
     static EncodeTiledFn2 encode = nullptr;
     if (encode == nullptr) {

@@ -67,6 +67,9 @@ class AttnDesc(C.Structure):
         ("dqkv", C.c_void_p),
         ("dalibi_scale", C.c_void_p),
         ("qk_bound", C.c_void_p),
+        ("bwd_algo", C.c_int),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -206,11 +209,28 @@ def attn_fwd(qkv, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None,
     return out, lse
 
 
+BWD_RESIDENT_MAX = 160  # tokens per sequence the shared-memory-resident backward takes (attention.cu BWD_LMAX)
+
+
 def attn_bwd(dout, qkv, out, lse, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None,
-             dalibi_scale=None, drop_p=0.0, seed=0):
+             dalibi_scale=None, drop_p=0.0, seed=0, algo=0, skip_far_keys=True):
+    """``algo``: 0 automatic (bf16: resident kernel up to 160 tokens, tiled kernel beyond), 1 resident, 2 tiled.
+    The tiled kernel runs as prepare -> backward -> finish (three launches) over a workspace allocated here."""
     assert dout.is_contiguous() and dout.dtype == qkv.dtype
     dqkv = torch.zeros_like(qkv) if qkv.dtype == torch.float32 else torch.empty_like(qkv)
+    tiled = qkv.dtype == torch.bfloat16 and (algo == 2 or (algo == 0 and seq > BWD_RESIDENT_MAX))
     d = AttnDesc()
+    d.bwd_algo = algo
+    if tiled:
+        lib = L.load()
+        lib.a2v_attn_bwd_workspace_bytes.restype = C.c_size_t
+        nbytes = int(lib.a2v_attn_bwd_workspace_bytes(batch, seq, heads))
+        ws = torch.empty((nbytes + 3) // 4, device=qkv.device, dtype=torch.float32)
+        d.workspace, d.workspace_bytes = _p(ws), nbytes
+        if skip_far_keys and pos is None and slopes is not None and seq > 256:
+            bound = torch.zeros(batch * heads * 2, device=qkv.device, dtype=torch.float32)
+            _call("a2v_attn_qk_bound", qkv, _p(qkv), _p(bound), batch, seq, heads)
+            d.qk_bound = _p(bound)
     d.dtype = L.dtype_code(qkv)
     d.batch, d.L, d.H, d.head_dim = batch, seq, heads, 64
     d.qkv, d.out, d.lse, d.pos = _p(qkv), _p(out), _p(lse), _p(pos)
@@ -219,6 +239,11 @@ def attn_bwd(dout, qkv, out, lse, batch, seq, heads, *, pos=None, slopes=None, a
     d.sm_scale = 64 ** -0.5
     d.drop_p, d.seed = drop_p, seed
     d.dout, d.dqkv, d.dalibi_scale = _p(dout), _p(dqkv), _p(dalibi_scale)
+    if tiled:
+        _call("a2v_attn_bwd_prepare", qkv, C.byref(d))
+        _call("a2v_attn_bwd", qkv, C.byref(d))
+        _call("a2v_attn_bwd_finish", qkv, C.byref(d))
+        return dqkv
     _call("a2v_attn_bwd", qkv, C.byref(d))
     return dqkv
 

@@ -315,11 +315,25 @@ typedef struct {
      * forward skips key tiles that ALiBi pushes below 2^-50 of the row maximum (their sum is far below fp32
      * resolution; the reference materialises and rounds them away, nn/modalities/modules.py:393-399). */
     const float* qk_bound;
+    /* backward, bf16: 0 = automatic (L <= 160: the shared-memory-resident kernel of the short student sequences;
+     * longer: the tiled kernel), 1 = resident, 2 = tiled. The tiled kernel (finetune path with full-length
+     * gradients, nn/wav2vec2.py:437-444; 48 kHz pretraining) needs a caller-owned workspace of
+     * a2v_attn_bwd_workspace_bytes() bytes, 16-byte aligned, and the call sequence
+     *   a2v_attn_bwd_prepare (delta = rowsum(dO * O), clears the fp32 dQ accumulator)
+     *   a2v_attn_bwd         (dK, dV written; dQ accumulated per key tile; qk_bound optional as in the forward)
+     *   a2v_attn_bwd_finish  (dQ scaled and rounded into dqkv)
+     * on one stream with the same descriptor. */
+    int bwd_algo;
+    void* workspace;
+    int64_t workspace_bytes;
 } a2v_attn_desc;
 
 int a2v_attn_qk_bound(const void* qkv_bf16, float* bound, int batch, int L, int H, a2v_stream_t stream);
 int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream);
+size_t a2v_attn_bwd_workspace_bytes(int batch, int L, int H);
+int a2v_attn_bwd_prepare(const a2v_attn_desc* d, a2v_stream_t stream);
 int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream);
+int a2v_attn_bwd_finish(const a2v_attn_desc* d, a2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * SincNet front end (nn/sinc.py:107-223,286-337). Channels-last output (B, N, 128) with the

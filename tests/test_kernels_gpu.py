@@ -174,13 +174,77 @@ def test_attention_fwd_bwd(dtype, batch, seq, heads, with_pos):
     out, lse = ops.attn_fwd(qkv, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale)
     tol = 2e-5 if dtype == torch.float32 else 1e-2
     assert _rel(out, ref) < tol, _rel(out, ref)
-    if seq <= 160 or dtype == torch.float32:
+    if True:  # every length: resident kernel up to 160 tokens, tiled kernel beyond (bf16); fp32 validation kernels
         dsc = torch.zeros(heads, device="cuda")
         dqkv = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale,
                             dalibi_scale=dsc)
         gt = 5e-5 if dtype == torch.float32 else 2e-2
         assert _rel(dqkv, qr.grad) < gt, _rel(dqkv, qr.grad)
         assert _rel(dsc, sr.grad) < max(gt, 1e-3), (dsc, sr.grad)
+
+
+@pytest.mark.parametrize("batch,seq,heads,with_pos,drop_p",
+                         [(3, 142, 4, True, 0.0), (2, 128, 2, False, 0.0), (2, 129, 2, True, 0.1), (2, 300, 2, False, 0.0),
+                          (2, 852, 4, True, 0.0), (1, 1000, 2, True, 0.2), (2, 2000, 16, False, 0.0), (1, 2100, 3, False, 0.1)])
+def test_attention_backward_tiled_any_length(batch, seq, heads, with_pos, drop_p):
+    """The tiled backward (key tiles resident, query tiles streamed, dQ through fp32 atomics; finetune path and 48 kHz
+    student) against fp32 torch autograd: ragged lengths, token positions, the ALiBi window on contiguous sequences,
+    and attention dropout with the kernel's own keep mask (forward and backward regenerate the same hashes). Forced
+    (algo=2) also on the short lengths the resident kernel normally takes, where both kernels must agree."""
+    from animal2vec_b200 import ops
+
+    d = heads * 64
+    seed = 0x1234ABCD99
+    qkv = torch.randn(batch, seq, 3 * d, device="cuda", generator=_g(1)).bfloat16()
+    pos = None
+    if with_pos:
+        pos = torch.stack([torch.randperm(12000, device="cuda", generator=_g(10 + i))[:seq].sort().values
+                           for i in range(batch)]).to(torch.int32).contiguous()
+    slopes = torch.tensor([2.0 ** (-8.0 * (h + 1) / heads) for h in range(heads)], device="cuda")
+    scale = torch.rand(heads, device="cuda", generator=_g(2)) + 0.5
+    if heads > 2:
+        scale[1] = 0.0  # a head without ALiBi: no window, clamp gate on its scale gradient
+    dout = torch.randn(batch, seq, d, device="cuda", generator=_g(3)).bfloat16()
+    out, lse = ops.attn_fwd(qkv, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=drop_p, seed=seed,
+                            skip_far_keys=True)
+
+    qr = qkv.float().clone().requires_grad_(True)
+    sr = scale.clone().requires_grad_(True)
+    q, k, v = qr.view(batch, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = (q * 64 ** -0.5) @ k.transpose(-1, -2)
+    p_ = pos.float() if pos is not None else torch.arange(seq, device="cuda").float().expand(batch, seq)
+    dist = (p_[:, :, None] - p_[:, None, :]).abs()
+    s = s - (slopes * sr.clamp_min(0)).view(1, heads, 1, 1) * dist[:, None]
+    a = s.softmax(-1)
+    if drop_p > 0:
+        keep = torch.zeros(batch, heads, seq, seq, device="cuda", dtype=torch.bool)
+        for c0 in range(0, seq, 64):  # read the mask out through the forward's linearity in V (uniform attention)
+            z = torch.zeros(batch, seq, 3 * d, device="cuda", dtype=torch.bfloat16)
+            n = min(64, seq - c0)
+            z[:, c0:c0 + n, 2 * d:] = torch.eye(64, device="cuda", dtype=torch.bfloat16)[:n].repeat(1, heads)
+            o, _ = ops.attn_fwd(z, batch, seq, heads, pos=pos, drop_p=drop_p, seed=seed)
+            keep[:, :, :, c0:c0 + n] = o.float().view(batch, seq, heads, 64).permute(0, 2, 1, 3)[..., :n] > 0.5 / seq
+        a = a * keep.float() / (1 - drop_p)
+    ref = (a @ v).transpose(1, 2).reshape(batch, seq, d)
+    ref.backward(dout.float())
+    assert _rel(out, ref) < 1e-2
+
+    dsc = torch.zeros(heads, device="cuda")
+    dqkv = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale,
+                        dalibi_scale=dsc, drop_p=drop_p, seed=seed, algo=2)
+    for part, name in ((slice(0, d), "dq"), (slice(d, 2 * d), "dk"), (slice(2 * d, 3 * d), "dv")):
+        e = _rel(dqkv[..., part], qr.grad[..., part])
+        assert e < 2e-2, (name, e)
+    assert _rel(dsc, sr.grad) < 2e-2, (dsc, sr.grad)
+    if seq <= 160:
+        dsc1 = torch.zeros(heads, device="cuda")
+        dq1 = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale,
+                           dalibi_scale=dsc1, drop_p=drop_p, seed=seed, algo=1)
+        assert _rel(dqkv, dq1) < 5e-3 and _rel(dsc, dsc1) < 5e-3
+    if pos is None and seq > 256:  # the window changes nothing measurable
+        dq_full = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, slopes=slopes, alibi_scale=scale, drop_p=drop_p,
+                               seed=seed, algo=2, skip_far_keys=False)
+        assert _rel(dqkv, dq_full) < 1e-3, _rel(dqkv, dq_full)
 
 
 @pytest.mark.parametrize("qk_scale,seq", [(1.0, 2000), (0.3, 2000), (6.0, 2000), (1.0, 1111), (1.0, 2500)])

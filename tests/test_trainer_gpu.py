@@ -107,7 +107,7 @@ def test_train_steps_match_an_oracle_optimizer_loop():
     ocfg = O.tiny_config()
     cfg = Cfg.no_randomness(Cfg.tiny())
     params = O.init_params(ocfg, 0)
-    oc = OptimConfig(lr=2e-3, warmup_updates=2, max_update=50, weight_decay=0.01, clip_norm=1.0)
+    oc = OptimConfig(lr=2e-3, warmup_updates=2, warmup_init_lr=5e-4, max_update=50, weight_decay=0.01, clip_norm=1.0)
     eng = PretrainEngine(cfg, "cuda", precision="fp32", init=params)
     tr = PretrainTrainer(eng, oc)
 
@@ -153,4 +153,8 @@ def test_train_steps_match_an_oracle_optimizer_loop():
         assert _rel(upd_g, upd_o) < 1e-2, (step, _rel(upd_g, upd_o))
         ema_g = torch.cat([(eng.E.view(k).cpu() - params[k]).reshape(-1) for k in teacher])
         ema_o = torch.cat([(teacher[k] - params[k]).reshape(-1) for k in teacher])
-        assert _rel(ema_g, ema_o) < 1e-2, (step, _rel(ema_g, ema_o))
+        # the EMA moves the shadow by (1 - tau) * update ~ 1e-7 of the parameter values: fp32 rounding of
+        # tau * E + (1 - tau) * S (different operation order on the two sides) is a visible floor
+        p0 = torch.cat([params[k].reshape(-1) for k in teacher])
+        err = float((ema_g.double() - ema_o.double()).norm())
+        assert err <= 1e-2 * float(ema_o.double().norm()) + 3e-7 * float(p0.double().norm()), (step, err)
