@@ -265,6 +265,104 @@ def tiny(**kw) -> Data2VecMultiConfig:
     return resolve(c)
 
 
+@dataclass
+class Wav2Vec2CcasFinetuneConfig:
+    """nn/wav2vec2.py:39-54 on top of fairseq's Wav2Vec2CtcConfig / Wav2Vec2AsrConfig (third party, absent from
+    /root/reference; field names and defaults restated from fairseq @ 920a548, models/wav2vec/wav2vec2_asr.py)."""
+
+    # ---- fairseq Wav2Vec2AsrConfig
+    w2v_path: Optional[str] = None
+    no_pretrained_weights: bool = False
+    dropout_input: float = 0.0
+    final_dropout: float = 0.0
+    dropout: float = 0.0
+    attention_dropout: float = 0.0
+    activation_dropout: float = 0.0
+    conv_feature_layers: Optional[str] = "[(512, 10, 5)] + [(512, 3, 2)] * 4 + [(512,2,2)] + [(512,2,2)]"
+    encoder_embed_dim: Optional[int] = 768
+    apply_mask: bool = False
+    mask_length: int = 10
+    mask_prob: float = 0.5
+    mask_selection: str = "static"
+    mask_other: float = 0
+    no_mask_overlap: bool = False
+    mask_min_space: int = 1
+    require_same_masks: bool = True
+    mask_dropout: float = 0.0
+    mask_channel_length: int = 10
+    mask_channel_prob: float = 0.0
+    mask_channel_selection: str = "static"
+    mask_channel_other: float = 0
+    no_mask_channel_overlap: bool = False
+    freeze_finetune_updates: int = 0
+    feature_grad_mult: float = 0.0
+    layerdrop: float = 0.0
+    drop_path: float = 0
+    mask_channel_min_space: int = 1
+    mask_channel_before: bool = False
+    normalize: bool = True  # II("task.normalize")
+    update_alibi: bool = True
+    data: Optional[str] = None  # II("task.data")
+    w2v_args: Any = None
+    offload_activations: bool = False
+    min_params_to_wrap: int = int(1e8)
+    checkpoint_activations: bool = False
+    ddp_backend: Optional[str] = None  # II("distributed_training.ddp_backend")
+    zero_mask: bool = False
+    load_ema: bool = False
+    layer_decay: float = 1
+    # ---- fairseq Wav2Vec2CtcConfig
+    blank_weight: float = 0
+    blank_mode: str = "add"
+    # ---- nn/wav2vec2.py:39-54
+    unique_labels: Optional[str] = None  # II("task.unique_labels")
+    average_top_k_layers: int = 16
+    use_focal_loss: bool = True  # II("criterion.use_focal_loss")
+    sample_rate: int = 8000  # II("task.sample_rate")
+    mixup_prob: float = 0.5
+    mixing_window_length: float = 0.1
+    source_mixup: float = -1.0
+    same_mixup: bool = True
+    target_mixup: bool = True
+    gain_mode: str = "A_weighting"
+    load_pretrain_weights: bool = False
+
+
+def shipped_finetune(**kw) -> Wav2Vec2CcasFinetuneConfig:
+    """configs/MeerKAT/finetune_mixup_100.yaml:82-120 (model section)."""
+    d = dict(freeze_finetune_updates=10000, feature_grad_mult=0.0, apply_mask=True, average_top_k_layers=16,
+             mask_prob=0.825, mask_length=4, mask_channel_prob=0.5, mask_channel_length=64, dropout=0.1,
+             dropout_input=0.0, activation_dropout=0.1, attention_dropout=0.2, final_dropout=0.0, layerdrop=0.1,
+             drop_path=0.0, target_mixup=True, source_mixup=0.5, mixup_prob=1.0, same_mixup=True,
+             mixing_window_length=0.05, gain_mode="A_weighting", load_pretrain_weights=False,
+             unique_labels="['beep', 'synch', 'sn', 'cc', 'ld', 'oth', 'mo', 'al', 'soc', 'agg', 'eating', 'focal']")
+    d.update(kw)
+    return Wav2Vec2CcasFinetuneConfig(**d)
+
+
+def finetune_overrides(model_cfg: Data2VecMultiConfig, ft: Wav2Vec2CcasFinetuneConfig) -> Data2VecMultiConfig:
+    """The ``arg_overrides`` Wav2VecEncoderModOut applies to the pretraining config when it rebuilds the model from
+    the checkpoint (nn/wav2vec2.py:95-130), plus remove_pretraining_modules' clone_batch = 1 (nn/data2vec2.py:1127)."""
+    import copy
+
+    c = copy.deepcopy(model_cfg)
+    a = c.modalities.audio
+    c.encoder_dropout = c.post_mlp_drop = a.prenet_dropout = ft.dropout
+    c.activation_dropout = ft.activation_dropout
+    c.dropout_input = ft.dropout_input
+    c.attention_dropout = ft.attention_dropout
+    c.layerdrop = a.prenet_layerdrop = ft.layerdrop
+    c.start_drop_path_rate = c.end_drop_path_rate = ft.drop_path
+    a.mask_length, a.mask_prob, a.mask_dropout = ft.mask_length, ft.mask_prob, ft.mask_dropout
+    a.mask_channel_length, a.mask_channel_prob = ft.mask_channel_length, ft.mask_channel_prob
+    a.encoder_zero_mask = ft.zero_mask
+    a.inverse_mask = False
+    a.local_grad_mult = ft.feature_grad_mult
+    a.learned_alibi_scale = ft.update_alibi
+    c.clone_batch = 1
+    return resolve(c)
+
+
 def no_randomness(cfg: Data2VecMultiConfig) -> Data2VecMultiConfig:
     """The deterministic "stage parity" setting: dropouts, mask-token noise and mixup off."""
     cfg.encoder_dropout = cfg.post_mlp_drop = cfg.attention_dropout = cfg.activation_dropout = 0.0

@@ -77,9 +77,11 @@ class _Weights:
 
 class PretrainEngine:
     def __init__(self, cfg: Data2VecMultiConfig, device="cuda", precision: str = "bf16",
-                 init: Optional[Dict[str, torch.Tensor]] = None, init_seed: int = 0, rng_seed: int = 0):
+                 init: Optional[Dict[str, torch.Tensor]] = None, init_seed: int = 0, rng_seed: int = 0,
+                 finetune: bool = False):
         cfg = resolve(cfg)
-        self._check_supported(cfg)
+        self._check_supported(cfg, finetune=finetune)
+        self.finetune = finetune
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         L.load()  # fail loudly if the CUDA library is not built: there is no other implementation
@@ -138,14 +140,17 @@ class PretrainEngine:
 
     # ------------------------------------------------------------------------------------ support matrix
     @staticmethod
-    def _check_supported(cfg: Data2VecMultiConfig) -> None:
+    def _check_supported(cfg: Data2VecMultiConfig, finetune: bool = False) -> None:
+        """``finetune``: the variants the finetune wrapper switches on through its arg_overrides
+        (nn/wav2vec2.py:95-130: layerdrop, activation dropout, noise mask tokens, channel masking, frozen feature
+        extractor) are accepted; they are implemented by animal2vec_b200.finetune.FinetuneEngine only."""
         a = cfg.modalities.audio
         bad = []
         if cfg.layer_norm_first: bad.append("layer_norm_first=True")
-        if cfg.layerdrop or a.prenet_layerdrop: bad.append("layerdrop>0")
+        if (cfg.layerdrop or a.prenet_layerdrop) and not finetune: bad.append("layerdrop>0")
         if cfg.start_drop_path_rate or cfg.end_drop_path_rate or a.start_drop_path_rate or a.end_drop_path_rate:
             bad.append("drop_path>0")
-        if cfg.activation_dropout: bad.append("activation_dropout>0")
+        if cfg.activation_dropout and not finetune: bad.append("activation_dropout>0")
         if cfg.dropout_input: bad.append("dropout_input>0")
         if cfg.end_of_block_targets: bad.append("end_of_block_targets")
         if not cfg.instance_norm_target_layer or cfg.layer_norm_target_layer or cfg.batch_norm_target_layer:
@@ -161,12 +166,14 @@ class PretrainEngine:
         if not a.use_alibi_encoder or a.learned_alibi or a.learned_alibi_scale_per_layer:
             bad.append("ALiBi variant other than the (learned per-head / global) scale")
         if a.num_extra_tokens: bad.append("num_extra_tokens>0")
-        if a.inverse_mask or a.mask_channel_prob or a.keep_masked_pct or a.remove_masks or a.mask_prob_min is not None:
+        if a.inverse_mask or a.keep_masked_pct or a.remove_masks or a.mask_prob_min is not None:
             bad.append("mask variant")
+        if a.mask_channel_prob and not finetune: bad.append("mask_channel_prob>0")
         if a.mask_length == 1: bad.append("mask_length=1 (random_masking branch, base.py:394-395)")
-        if not a.encoder_zero_mask: bad.append("encoder_zero_mask=False")
+        if not a.encoder_zero_mask and not finetune: bad.append("encoder_zero_mask=False")
         if a.ema_local_encoder: bad.append("ema_local_encoder")
-        if a.local_grad_mult != 1.0: bad.append("local_grad_mult != 1")
+        if a.local_grad_mult != (0.0 if finetune else 1.0):
+            bad.append("local_grad_mult other than 1 (pretraining) / 0 (finetune, feature_grad_mult: 0.0)")
         if a.conv_pos_pre_ln: bad.append("conv_pos_pre_ln")
         d = a.decoder
         if d is None or d.add_positions_masked or d.add_positions_all or d.projection_layers != 1 or not d.decoder_residual:
@@ -400,7 +407,7 @@ class PretrainEngine:
         return self.S.gview(name)
 
     # ------------------------------------------------------------------------------------ stages: forward
-    def _mixup(self, x: torch.Tensor) -> torch.Tensor:
+    def _mixup(self, x: torch.Tensor, info: Optional[dict] = None) -> torch.Tensor:
         """nn/data2vec2.py:536-598 (same_mixup, mixup_prob = 1, A-weighted gain). The random draws come
         from torch's CPU generator in the reference's order: one uniform_ for r, then one randperm."""
         cfg = self.cfg
@@ -408,10 +415,14 @@ class PretrainEngine:
         perm = ops.h2d_async(torch.randperm(x.size(0)).to(torch.int32), self.device)
         gain = ops.mixup_gain(x, self.hann, self.aweight, self.n_fft, self.n_fft // 2)
         mixed, _ = ops.mixup_apply(x, perm, gain, r)
+        if info is not None:  # the finetune path mixes the targets with the same draw (nn/wav2vec2.py:424-431)
+            info["perm"], info["r"] = perm, r
         return mixed
 
-    def _fe_forward(self, x: torch.Tensor, c: SimpleNamespace, save: bool) -> torch.Tensor:
-        """SincConv + conv stack + project_features -> local_features (B, T, D)."""
+    def _fe_forward(self, x: torch.Tensor, c: SimpleNamespace, save: bool, save_proj: bool = False) -> torch.Tensor:
+        """SincConv + conv stack + project_features -> local_features (B, T, D). ``save_proj`` (with save False):
+        keep only what the backward of project_features needs (frozen conv extractor, local_grad_mult = 0:
+        base.py:205-207 puts just ``local_encoder`` under no_grad, the projection still trains)."""
         W = self.WS
         le = ENC + "local_encoder.conv_layers."
         c0, k0, _ = self.layers[0]
@@ -447,11 +458,12 @@ class PretrainEngine:
         clast = self.layers[-1][0]
         cfgp = ops.RowLnCfg(clast, 1e-5)
         lnp, m, r = ops.rowln_fwd(cfgp, fe[-1].a, None, W.f32[ENC + "project_features.1.weight"],
-                                  W.f32[ENC + "project_features.1.bias"], save_stats=save)
+                                  W.f32[ENC + "project_features.1.bias"], save_stats=save or save_proj)
         lf = self.lin(lnp, W, ENC + "project_features.2.weight", bias=W.f32[ENC + "project_features.2.bias"])
         if save:
             c.fe, c.filt, c.x = fe, filt, x
-            c.proj = SimpleNamespace(lnp=lnp, m=m, r=r, cfg=cfgp)
+        if save or save_proj:
+            c.proj = SimpleNamespace(lnp=lnp, m=m, r=r, cfg=cfgp, a=fe[-1].a)
         return lf
 
     def _posconv_forward(self, W: _Weights, x: torch.Tensor, save: Optional[list]) -> torch.Tensor:
@@ -484,13 +496,18 @@ class PretrainEngine:
                                    training=train, save_stats=save is not None)
         u = torch.empty(rows * seq, self.hidden, device=x.device, dtype=self.adt) if save is not None else None
         h = self.lin(x1, W, pre + "mlp.fc1.weight", bias=f[pre + "mlp.fc1.bias"], act=1, preact=u)
+        p_mlp = cfg.activation_dropout if train else 0.0  # timm Mlp drop1 (= mlp_drop, modules.py:312-317)
+        s_mlp = self._seed(site + 3)
+        if p_mlp > 0:
+            h = ops.row_gather(h, self._arange(rows * seq), rows * seq, drop_p=p_mlp, drop_seed=s_mlp)
         t = self.lin(h, W, pre + "mlp.fc2.weight", bias=f[pre + "mlp.fc2.bias"])
         c2 = ops.RowLnCfg(d, cfg.norm_eps, drop_b=cfg.post_mlp_drop)
         x2, m2, r2 = ops.rowln_fwd(c2, x1, t, f[pre + "norm2.weight"], f[pre + "norm2.bias"], seed_b=s2,
                                    training=train, save_stats=save is not None)
         if save is not None:
             save.append(SimpleNamespace(pre=pre, x=x, qkv=qkv, ao=ao, lse=lse, pr=pr, x1=x1, m1=m1, r1=r1, u=u, h=h,
-                                        t=t, m2=m2, r2=r2, s_att=s_att, s1=s1, s2=s2, p_att=p_att, c1=c1, c2=c2))
+                                        t=t, m2=m2, r2=r2, s_att=s_att, s1=s1, s2=s2, p_att=p_att, c1=c1, c2=c2,
+                                        p_mlp=p_mlp, s_mlp=s_mlp))
         return x2, t
 
     def _encoder_forward(self, W: _Weights, x, rows, seq, pos, train, save: Optional[list], targets: Optional[list],
@@ -672,13 +689,27 @@ class PretrainEngine:
         return t[:n]
 
     # ------------------------------------------------------------------------------------ backward
-    def _block_backward(self, W: _Weights, s: SimpleNamespace, dx2, rows, seq, pos, train: bool):
+    def _block_backward(self, W: _Weights, s: SimpleNamespace, dx2, rows, seq, pos, train: bool, extra_dt=None):
+        """``extra_dt``: additional gradient of the block's FFN output ``t`` (the finetune head averages the FFN
+        outputs of the top-k blocks, nn/wav2vec2.py:446-462); ``dx2`` None: the block output itself is unused."""
         pre, G, f = s.pre, self.G, W.f32
-        dz2, dt = ops.rowln_bwd(s.c2, dx2, s.x1, s.t, f[pre + "norm2.weight"], f[pre + "norm2.bias"], None, None,
-                                s.m2, s.r2, seed_b=s.s2, training=train, dgamma=G(pre + "norm2.weight"),
-                                dbeta=G(pre + "norm2.bias"), dbias_b=G(pre + "mlp.fc2.bias"))
+        if dx2 is None:
+            assert extra_dt is not None
+            dz2, dt = None, extra_dt
+            ops.colsum(dt, G(pre + "mlp.fc2.bias"))
+        else:
+            dz2, dt = ops.rowln_bwd(s.c2, dx2, s.x1, s.t, f[pre + "norm2.weight"], f[pre + "norm2.bias"], None, None,
+                                    s.m2, s.r2, seed_b=s.s2, training=train, dgamma=G(pre + "norm2.weight"),
+                                    dbeta=G(pre + "norm2.bias"),
+                                    dbias_b=G(pre + "mlp.fc2.bias") if extra_dt is None else None)
+            if extra_dt is not None:
+                dt = self._add(dt, extra_dt)
+                ops.colsum(dt, G(pre + "mlp.fc2.bias"))
         self.wgrad(dt, s.h, G(pre + "mlp.fc2.weight"))
-        du = ops.dgelu_mul(self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True), s.u, colsum=G(pre + "mlp.fc1.bias"))
+        dh = self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True)
+        if getattr(s, "p_mlp", 0.0) > 0:
+            dh = ops.row_gather(dh, self._arange(rows * seq), rows * seq, drop_p=s.p_mlp, drop_seed=s.s_mlp)
+        du = ops.dgelu_mul(dh, s.u, colsum=G(pre + "mlp.fc1.bias"))
         self.wgrad(du, s.x1, G(pre + "mlp.fc1.weight"))
         dx1 = self.lin(du, W, pre + "mlp.fc1.weight", dgrad=True, residual=dz2)
         del du, dz2, dt
@@ -762,18 +793,25 @@ class PretrainEngine:
         return ops.row_gather(a.view(-1, a.shape[-1]), self._arange(n // a.shape[-1]), n // a.shape[-1],
                               add=b.view(-1, a.shape[-1]), out_shape=a.shape)
 
-    def _fe_backward(self, c: SimpleNamespace, dlf: torch.Tensor) -> None:
+    def _proj_backward(self, c: SimpleNamespace, dlf: torch.Tensor) -> torch.Tensor:
+        """Backward of project_features (LayerNorm(C) + Linear(C -> D), audio.py:83-88): parameter gradients and the
+        gradient of the conv extractor's output."""
         W, G = self.WS, self.G
-        le = ENC + "local_encoder.conv_layers."
         n = ENC + "project_features.2.weight"
         ops.colsum(dlf, G(ENC + "project_features.2.bias"))
         self.wgrad(dlf, c.proj.lnp, G(n))
         dl = self.lin(dlf, W, n, dgrad=True)
-        fe = c.fe
-        da, _ = ops.rowln_bwd(c.proj.cfg, dl.view(fe[-1].a.shape), fe[-1].a, None,
+        da, _ = ops.rowln_bwd(c.proj.cfg, dl.view(c.proj.a.shape), c.proj.a, None,
                               W.f32[ENC + "project_features.1.weight"], W.f32[ENC + "project_features.1.bias"], None,
                               None, c.proj.m, c.proj.r, dgamma=G(ENC + "project_features.1.weight"),
                               dbeta=G(ENC + "project_features.1.bias"))
+        return da
+
+    def _fe_backward(self, c: SimpleNamespace, dlf: torch.Tensor) -> None:
+        W, G = self.WS, self.G
+        le = ENC + "local_encoder.conv_layers."
+        fe = c.fe
+        da = self._proj_backward(c, dlf)
         for i in reversed(range(1, len(self.layers))):
             ch, k, st = self.layers[i]
             s, xin = fe[i], fe[i - 1].a

@@ -548,3 +548,68 @@ def mixup_apply(x, perm_i32, gain_db, r):
     p = torch.empty(b, device=x.device, dtype=torch.float32)
     _call("a2v_mixup_apply", x, _p(x), _p(perm_i32), _p(gain_db), b, n, gain_db.shape[1], C.c_float(r), _p(out), _p(p))
     return out, p
+
+
+# ----------------------------------------------------------------------------- finetune head / criterion
+def layer_mean_head_fwd(layers: Sequence[torch.Tensor], w: torch.Tensor, bias: Optional[torch.Tensor],
+                        save_mean: bool = True):
+    """(logits (rows, C) fp32, xmean (rows, D) or None): mean over the given layer outputs, then Linear(D, C)."""
+    k = len(layers)
+    d_ = layers[0].shape[-1]
+    rows = layers[0].numel() // d_
+    for x in layers:
+        assert x.is_contiguous() and x.shape == layers[0].shape and x.dtype == layers[0].dtype
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] == d_
+    c = w.shape[0]
+    dev = layers[0].device
+    ptrs = h2d_async(torch.tensor([x.data_ptr() for x in layers], dtype=torch.int64), dev)
+    xmean = torch.empty(rows, d_, device=dev, dtype=layers[0].dtype) if save_mean else None
+    logits = torch.empty(rows, c, device=dev, dtype=torch.float32)
+    _call("a2v_layer_mean_head_fwd", layers[0], L.dtype_code(layers[0]), _p(ptrs), k, C.c_int64(rows), d_, c, _p(w),
+          _p(bias), _p(xmean), _p(logits))
+    return logits, xmean
+
+
+def head_bwd(dlogits: torch.Tensor, xmean: torch.Tensor, w: torch.Tensor, k: int, dw: torch.Tensor,
+             db: Optional[torch.Tensor], want_g: bool = True) -> Optional[torch.Tensor]:
+    rows, d_ = xmean.shape
+    c = w.shape[0]
+    assert dlogits.dtype == torch.float32 and dlogits.is_contiguous() and dlogits.numel() == rows * c
+    assert dw.dtype == torch.float32 and dw.shape == w.shape
+    g = torch.empty_like(xmean) if want_g else None
+    _call("a2v_head_bwd", xmean, L.dtype_code(xmean), _p(dlogits), _p(xmean), _p(w), k, C.c_int64(rows), d_, c, _p(g),
+          _p(dw), _p(db))
+    return g
+
+
+def focal_loss_fwd(logits, targets, *, perm=None, rows_per_clip=0, r=1.0, alpha=0.25, gamma=2.0, threshold=0.5,
+                   want_unreduced=False, want_mixed_targets=False):
+    """Returns (loss_sum double[1], counters int64[5] = tp/fp/tn/fn/n_correct, unreduced loss or None, mixed targets or
+    None)."""
+    rows, c = logits.shape
+    assert logits.dtype == torch.float32 and targets.dtype == torch.float32 and logits.is_contiguous()
+    assert targets.is_contiguous() and targets.numel() == logits.numel()
+    dev = logits.device
+    loss_sum = torch.zeros(1, device=dev, dtype=torch.float64)
+    counters = torch.zeros(5, device=dev, dtype=torch.int64)
+    un = torch.empty_like(logits) if want_unreduced else None
+    mt = torch.empty_like(logits) if want_mixed_targets else None
+    _call("a2v_focal_loss_fwd", logits, _p(logits), _p(targets), _p(perm), C.c_int64(rows), c, int(rows_per_clip),
+          C.c_float(r), C.c_float(alpha), C.c_float(gamma), C.c_float(threshold), _p(loss_sum), _p(un), _p(mt),
+          _p(counters))
+    return loss_sum, counters, un, mt
+
+
+def focal_loss_bwd(logits, targets, *, perm=None, rows_per_clip=0, r=1.0, alpha=0.25, gamma=2.0, grad_out=None):
+    rows, c = logits.shape
+    dlogits = torch.empty_like(logits)
+    _call("a2v_focal_loss_bwd", logits, _p(logits), _p(targets), _p(perm), C.c_int64(rows), c, int(rows_per_clip),
+          C.c_float(r), C.c_float(alpha), C.c_float(gamma), _p(grad_out), _p(dlogits))
+    return dlogits
+
+
+def channel_mask_(x: torch.Tensor, chmask_u8: torch.Tensor, rows_per_clip: int) -> torch.Tensor:
+    d_ = x.shape[-1]
+    assert x.is_contiguous() and chmask_u8.dtype == torch.uint8 and chmask_u8.shape[-1] == d_
+    _call("a2v_channel_mask", x, L.dtype_code(x), _p(x), _p(chmask_u8), C.c_int64(x.numel() // d_), int(rows_per_clip), d_)
+    return x

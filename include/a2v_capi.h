@@ -370,6 +370,33 @@ int a2v_mixup_gain(const float* x, const float* hann, const float* aweight, int 
 int a2v_mixup_apply(const float* x, const int32_t* perm, const float* gain_db, int B, int N, int W, float r,
                     float* out, float* p_out, a2v_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Finetune head and criterion (BASELINE configs[3]).
+ *   a2v_layer_mean_head_fwd: x = mean of the top-k FFN outputs, logits = proj(x) (nn/wav2vec2.py:446-464).
+ *     layers = DEVICE table of K row-major (rows, D) pointers; W (C, D) / bias (C) fp32; xmean (rows, D, same dtype,
+ *     optional) keeps the averaged input for the backward; logits (rows, C) fp32.
+ *   a2v_head_bwd: g (rows, D, optional) = dlogits W / K (what each averaged layer output receives),
+ *     dW += dlogits^T xmean, db += colsum(dlogits)  (fp32 accumulators).
+ *   a2v_focal_loss_fwd/_bwd: sigmoid focal loss on logits (nn/utils.py:971-1010; alpha < 0 disables the class
+ *     weighting) with the target mixup of nn/wav2vec2.py:424-431 folded in (perm = partner clip per clip, r = mixing
+ *     weight; perm NULL = plain targets). loss_sum (double, accumulated), optional unreduced loss / mixed targets,
+ *     counters[5] = {tp, fp, tn, fn, n_correct} of nn/criterions.py:198-229 + nn/utils.py:925-969 (multi-label
+ *     branch, sigmoid >= threshold against the int64-truncated target), accumulated. grad_out: device scalar or NULL.
+ *   a2v_channel_mask: x[b, t, c] = 0 where chmask[b, c] (nn/modalities/base.py:470-484), in place.
+ * ------------------------------------------------------------------------------------ */
+int a2v_layer_mean_head_fwd(int dtype, const void* const* layers, int K, int64_t rows, int D, int C, const float* W,
+                            const float* bias, void* xmean, float* logits, a2v_stream_t stream);
+int a2v_head_bwd(int dtype, const float* dlogits, const void* xmean, const float* W, int K, int64_t rows, int D, int C,
+                 void* g, float* dW, float* db, a2v_stream_t stream);
+int a2v_focal_loss_fwd(const float* logits, const float* targets, const int32_t* perm, int64_t rows, int C,
+                       int rows_per_clip, float r, float alpha, float gamma, float threshold, double* loss_sum,
+                       float* loss_out, float* mixed_targets, uint64_t* counters, a2v_stream_t stream);
+int a2v_focal_loss_bwd(const float* logits, const float* targets, const int32_t* perm, int64_t rows, int C,
+                       int rows_per_clip, float r, float alpha, float gamma, const float* grad_out, float* dlogits,
+                       a2v_stream_t stream);
+int a2v_channel_mask(int dtype, void* x, const uint8_t* chmask, int64_t rows, int rows_per_clip, int D,
+                     a2v_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

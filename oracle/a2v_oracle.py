@@ -259,9 +259,16 @@ def feature_extractor(p: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, t
     return x
 
 
-def local_features(p: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, taps: Optional[dict] = None) -> Tensor:
-    """ModalitySpecificEncoder.local_features (base.py:194-213) + project_features (audio.py:83-88)."""
-    x = feature_extractor(p, cfg, source, taps).transpose(1, 2)
+def local_features(p: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, taps: Optional[dict] = None,
+                   frozen_extractor: bool = False) -> Tensor:
+    """ModalitySpecificEncoder.local_features (base.py:194-213) + project_features (audio.py:83-88).
+    ``frozen_extractor``: local_grad_mult = 0 -- ONLY the conv extractor runs under no_grad (base.py:205-207);
+    project_features (LayerNorm + Linear) keeps its gradient."""
+    if frozen_extractor:
+        with torch.no_grad():
+            x = feature_extractor(p, cfg, source, taps).transpose(1, 2)
+    else:
+        x = feature_extractor(p, cfg, source, taps).transpose(1, 2)
     c = x.shape[-1]
     x = F.layer_norm(x, (c,), p[ENC + "project_features.1.weight"], p[ENC + "project_features.1.bias"], 1e-5)
     return F.linear(x, p[ENC + "project_features.2.weight"], p[ENC + "project_features.2.bias"])
@@ -556,6 +563,44 @@ def finetune_logits(student: Dict[str, Tensor], cfg: OracleConfig, source: Tenso
     lrs = res["layer_results"][-k:]
     x = sum(lrs) / len(lrs)
     return F.linear(x, proj_w, proj_b)
+
+
+def finetune_features(student: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, *,
+                      time_mask: Optional[Tensor] = None, channel_mask: Optional[Tensor] = None) -> List[Tensor]:
+    """Data2VecMultiModel.forward(features_only=True, mask=True) in TRAIN mode with every dropout, layerdrop and the
+    mask-token noise at 0 (data2vec2.py:632-728; base.py:215-344 with clone_batch 1 / remove_masked False): the
+    conv extractor runs without gradient (local_grad_mult 0, base.py:205-207; project_features still trains), masked frames are replaced by
+    N(0, 0) = 0 tokens (encoder_zero_mask False, base.py:465-469), masked channels are zeroed (:470-484), then
+    x + positional_encoder(x), prenet, main blocks. Returns the FFN outputs of the main blocks (with autograd graph).
+    Pinned by tests/golden/tiny_finetune.npz (the reference's own forward + backward)."""
+    lf = local_features(student, cfg, source, frozen_extractor=True)
+    x = lf.clone()
+    if time_mask is not None:
+        x = x.masked_fill(time_mask[:, :, None], 0.0)
+    if channel_mask is not None:
+        x = x.masked_fill(channel_mask[:, None, :], 0.0)
+    b, t, _ = x.shape
+    pos = torch.arange(t).unsqueeze(0).expand(b, -1)
+    bias = alibi_bias(cfg, student[ENC + "alibi_scale"], pos)
+    x = x + positional_encoder(student, cfg, x)
+    x = prenet(student, cfg, x, bias)
+    layer_results = []
+    for j in range(cfg.depth):
+        x, ffn = alt_block(student, f"blocks.{j}.", x, bias, cfg)
+        layer_results.append(ffn)
+    return layer_results
+
+
+def finetune_loss(student: Dict[str, Tensor], cfg: OracleConfig, source: Tensor, target: Tensor, proj_w: Tensor,
+                  proj_b: Tensor, *, time_mask: Optional[Tensor] = None, channel_mask: Optional[Tensor] = None,
+                  top_k: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+    """Wav2VecEncoderModOut.forward (wav2vec2.py:437-482, unfrozen phase, mixup off) + the focal branch of
+    FinetuneCrossEntropyCriterion.forward (criterions.py:231-246, reduce=True): (summed loss, logits)."""
+    lrs = finetune_features(student, cfg, source, time_mask=time_mask, channel_mask=channel_mask)
+    k = top_k or cfg.average_top_k_layers
+    top = lrs[-k:]
+    logits = F.linear(sum(top) / len(top), proj_w, proj_b)
+    return sigmoid_focal_loss(logits, target, reduction="sum"), logits
 
 
 def sigmoid_focal_loss(inputs: Tensor, targets: Tensor, alpha: float = 0.25, gamma: float = 2.0,

@@ -1,0 +1,303 @@
+"""GPU parity of the finetune path (BASELINE configs[3]) through the C-ABI:
+kernels (top-k mean + head, focal loss with target mixup + confusion counters, channel mask) against torch / the oracle,
+and animal2vec_b200.finetune.FinetuneEngine against the reference's own golden vectors
+(tests/golden/tiny_features.npz: eval-mode logits / focal loss / confusion; tests/golden/tiny_finetune.npz: the masked
+training step with its gradients) and against the oracle's full tensors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import a2v_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _g(seed=0):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def _load(name):
+    return dict(np.load(os.path.join(GOLD, name), allow_pickle=False))
+
+
+@pytest.mark.parametrize("dtype,rows,d,c,k", [(torch.float32, 333, 128, 12, 2), (torch.bfloat16, 4000, 1024, 12, 16),
+                                              (torch.bfloat16, 257, 256, 20, 3)])
+def test_layer_mean_head_forward_backward(dtype, rows, d, c, k):
+    from animal2vec_b200 import ops
+
+    layers = [torch.randn(rows, d, device="cuda", generator=_g(i)).to(dtype) for i in range(k)]
+    w = torch.randn(c, d, device="cuda", generator=_g(50)) * 0.1
+    b = torch.randn(c, device="cuda", generator=_g(51)) * 0.1
+    logits, xmean = ops.layer_mean_head_fwd(layers, w, b)
+    xm_ref = sum(l.float() for l in layers) / k
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert _rel(xmean, xm_ref) < tol
+    ref = F.linear(xmean.float(), w, b)  # the head multiplies the stored (rounded) mean
+    assert _rel(logits, ref) < 1e-5
+    assert _rel(logits, F.linear(xm_ref, w, b)) < (1e-5 if dtype == torch.float32 else 1e-2)
+    dl = torch.randn(rows, c, device="cuda", generator=_g(60))
+    dw, db = torch.zeros_like(w), torch.zeros_like(b)
+    g = ops.head_bwd(dl, xmean, w, k, dw, db)
+    assert _rel(g, dl @ w / k) < tol
+    assert _rel(dw, dl.t() @ xmean.float()) < 1e-4
+    assert _rel(db, dl.sum(0)) < 1e-5
+    dw2 = torch.zeros_like(w)
+    assert ops.head_bwd(dl, xmean, w, k, dw2, None, want_g=False) is None  # frozen phase: head gradients only
+    assert _rel(dw2, dw) < 1e-5
+
+
+@pytest.mark.parametrize("mix", [False, True])
+def test_focal_loss_counters_and_gradient(mix):
+    from animal2vec_b200 import ops
+
+    bsz, t, c = 4, 250, 12
+    logits = (torch.randn(bsz * t, c, device="cuda", generator=_g(1)) * 2).contiguous()
+    target = (torch.rand(bsz * t, c, device="cuda", generator=_g(2)) < 0.15).float()
+    perm = r = None
+    tmix = target
+    if mix:  # nn/wav2vec2.py:424-431: target * r + (1 - r) * target[perm]
+        perm = torch.tensor([2, 0, 3, 1], device="cuda", dtype=torch.int32)
+        r = 0.7
+        tv = target.view(bsz, t, c)
+        tmix = (tv * r + (1 - r) * tv[perm.long()]).reshape(bsz * t, c)
+    lr = logits.clone().requires_grad_(True)
+    ref = O.sigmoid_focal_loss(lr, tmix, reduction="none")
+    ref.sum().backward()
+    loss_sum, counters, un, mt = ops.focal_loss_fwd(logits, target, perm=perm, rows_per_clip=t, r=r or 1.0,
+                                                    threshold=0.3, want_unreduced=True, want_mixed_targets=True)
+    assert _rel(un, ref.detach()) < 1e-5 and abs(float(loss_sum) - float(ref.sum())) <= 1e-5 * float(ref.sum())
+    assert _rel(mt, tmix) < 1e-6
+    # counters: the reference truncates the (possibly soft) target to int64 (criterions.py:196) and divides (utils.py:925-969)
+    pred = torch.where(torch.sigmoid(logits) < 0.3, 0, 1)
+    ti = tmix.to(torch.int64)
+    cv = pred / ti
+    want = [int((cv == 1).sum()), int((cv == float("inf")).sum()), int(torch.isnan(cv).sum()), int((cv == 0).sum()),
+            int(pred.eq(ti).sum())]
+    assert counters.tolist() == want, (counters.tolist(), want)
+    if not mix:
+        assert tuple(want[:4]) == O.confusion_counts(logits, target, 0.3)
+    go = torch.full((1,), 0.5, device="cuda")
+    dl = ops.focal_loss_bwd(logits, target, perm=perm, rows_per_clip=t, r=r or 1.0, grad_out=go)
+    assert _rel(dl, 0.5 * lr.grad) < 1e-5
+
+
+def test_channel_mask():
+    from animal2vec_b200 import ops
+
+    b, t, d = 3, 50, 128
+    for dtype in (torch.float32, torch.bfloat16):
+        x = torch.randn(b * t, d, device="cuda", generator=_g(3)).to(dtype)
+        cm = torch.rand(b, d, device="cuda", generator=_g(4)) < 0.3
+        ref = x.view(b, t, d).masked_fill(cm[:, None, :], 0).view(b * t, d)
+        out = ops.channel_mask_(x.clone(), cm.to(torch.uint8), t)
+        assert torch.equal(out, ref)
+
+
+def _engine(precision, ft_kw=None, seed_w=0):
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200.finetune import FinetuneEngine
+
+    ft = Cfg.shipped_finetune(dropout=0.0, activation_dropout=0.0, attention_dropout=0.0, layerdrop=0.0, source_mixup=-1.0,
+                              average_top_k_layers=2, freeze_finetune_updates=0, mask_channel_length=16)
+    for k, v in (ft_kw or {}).items():
+        setattr(ft, k, v)
+    params = O.init_params(O.tiny_config(), seed_w)
+    gen = torch.Generator().manual_seed(9)
+    w = torch.randn(12, 128, generator=gen) * 0.2
+    bias = torch.randn(12, generator=gen) * 0.1
+    eng = FinetuneEngine(Cfg.no_randomness(Cfg.tiny()), ft, 12, "cuda", precision=precision, init=params,
+                         head_init={"proj.weight": w, "proj.bias": bias}, metric_threshold=0.5)
+    return eng, params, w, bias, gen
+
+
+def test_eval_logits_loss_confusion_match_reference_fixture():
+    g = _load("tiny_features.npz")
+    eng, params, w, bias, gen = _engine("fp32")
+    b, n = int(g["b"]), int(g["n"])
+    x = F.layer_norm(torch.randn(b, n, generator=torch.Generator().manual_seed(int(g["seed_x"]))), (n,))
+    res0 = eng.forward(x.cuda(), None, training=False)
+    logits = res0["encoder_out"]
+    assert _rel(logits.cpu()[:, ::7, :], g["logits"]) < 1e-3
+    target = (torch.rand(logits.shape, generator=gen) < 0.15).float()
+    res = eng.forward(x.cuda(), target.cuda(), training=False, want_unreduced=True)
+    assert abs(float(res["loss_sum"]) - float(g["focal_sum"])) <= 1e-3 * float(g["focal_sum"])
+    assert _rel(res["loss_unreduced"].view(b, -1, 12).cpu()[:, ::7, :], g["focal_none"]) < 1e-3
+    assert res["counters"][:4].tolist() == [int(v) for v in g["confusion"]]
+    assert len(res["layer_results"]) == int(g["n_layers"])
+    for i in range(int(g["n_layers"])):
+        assert _rel(res["layer_results"][i].float().cpu()[:, ::7, ::5], g[f"layer{i}"]) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_matches_reference_golden_and_oracle(precision):
+    g = _load("tiny_finetune.npz")
+    cfg = O.tiny_config()
+    eng, params, w, bias, gen = _engine(precision)
+    b, n, t, classes = int(g["b"]), int(g["n"]), int(g["T"]), int(g["classes"])
+    x = F.layer_norm(torch.randn(b, n, generator=torch.Generator().manual_seed(int(g["seed_x"]))), (n,))
+    tm = np.unpackbits(g["time_mask"], axis=1)[:, :t].astype(bool)
+    cm = np.unpackbits(g["channel_mask"], axis=1)[:, : cfg.embed_dim].astype(bool)
+    target = (torch.rand(b, t, classes, generator=gen) < 0.15).float()
+    eng.zero_grad()
+    res = eng.forward(x.cuda(), target.cuda(), training=True, time_mask=tm, channel_mask=cm)
+    tol = 1e-3 if precision == "fp32" else 1e-2
+    gtol = 3e-3 if precision == "fp32" else 3e-2
+    assert _rel(res["encoder_out"].cpu()[:, ::7, :], g["logits"]) < tol * (1 if precision == "fp32" else 3)
+    loss = float(res["loss_sum"])
+    assert abs(loss - float(g["loss_sum"])) <= tol * float(g["loss_sum"]), (loss, float(g["loss_sum"]))
+    if precision == "fp32":
+        assert res["counters"].tolist() == [int(v) for v in g["confusion"]]
+    eng.backward()
+    for k, nrm in zip([str(k) for k in g["grad_keys"]], g["grad_norms"]):
+        got = float(eng.core.S.gview(k).double().norm())
+        assert abs(got - nrm) <= gtol * nrm + 1e-7, (k, got, nrm)
+    assert abs(float(eng.head_gw.double().norm()) - float(g["head_w_grad_norm"])) <= gtol * float(g["head_w_grad_norm"])
+    assert _rel(eng.head_gb.cpu(), g["head_b_grad"]) < gtol
+    pf = float(eng.core.S.gview(O.ENC + "project_features.2.weight").double().norm())
+    assert abs(pf - float(g["proj_feat_grad_norm"])) <= gtol * float(g["proj_feat_grad_norm"])
+    # the oracle's full gradients: every tensor that trains; frozen conv extractor and absent decoder stay at zero
+    student = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    wr, br = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    oloss, _ = O.finetune_loss(student, cfg, x, target, wr, br, time_mask=torch.from_numpy(tm),
+                               channel_mask=torch.from_numpy(cm))
+    oloss.backward()
+    assert _rel(eng.head_gw.cpu(), wr.grad) < gtol
+    for k, p in student.items():
+        got = eng.core.S.gview(k).float().cpu()
+        if p.grad is None:
+            assert float(got.abs().sum()) == 0.0, k
+        else:
+            assert _rel(got, p.grad) < gtol, (k, _rel(got, p.grad))
+
+
+def test_frozen_phase_trains_only_the_head():
+    eng, params, w, bias, gen = _engine("bf16", {"freeze_finetune_updates": 5})
+    g = _load("tiny_finetune.npz")
+    b, n, t = int(g["b"]), int(g["n"]), int(g["T"])
+    x = F.layer_norm(torch.randn(b, n, generator=torch.Generator().manual_seed(1)), (n,)).cuda()
+    target = (torch.rand(b, t, 12, generator=gen) < 0.15).float().cuda()
+    assert not eng.encoder_trainable
+    eng.zero_grad()
+    eng.forward(x, target, training=True)
+    eng.backward()
+    assert float(eng.core.S.grad.abs().sum()) == 0.0
+    assert float(eng.head_gw.abs().sum()) > 0 and float(eng.head_gb.abs().sum()) > 0
+    eng.num_updates = 5
+    assert eng.encoder_trainable
+    eng.zero_grad()
+    eng.forward(x, target, training=True)
+    eng.backward()
+    assert float(eng.core.S.grad.abs().sum()) > 0
+
+
+def test_shipped_regularisers_run_and_are_seed_deterministic():
+    """The shipped finetune recipe's stochastic pieces together (time + channel masks, noise tokens, dropout 0.1,
+    activation dropout 0.1, attention dropout 0.2, layerdrop 0.1, source + target mixup): finite, reproducible for
+    fixed seeds, different for another kernel seed."""
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200.finetune import FinetuneEngine
+
+    ft = Cfg.shipped_finetune(average_top_k_layers=2, freeze_finetune_updates=0, mask_channel_length=16, layerdrop=0.3)
+    params = O.init_params(O.tiny_config(), 0)
+    x = F.layer_norm(torch.randn(4, 16000, generator=torch.Generator().manual_seed(0)), (16000,)).cuda()
+    target = (torch.rand(4, 400, 12, generator=torch.Generator().manual_seed(1)) < 0.15).float().cuda()
+    outs = []
+    for seed in (3, 3, 4):
+        eng = FinetuneEngine(Cfg.tiny(), ft, 12, "cuda", precision="bf16", init=params, rng_seed=seed)
+        np.random.seed(11)
+        torch.manual_seed(5)
+        tm = np.zeros((4, 400), dtype=bool)
+        tm[:, 40:200] = True
+        cm = np.zeros((4, 128), dtype=bool)
+        cm[:, 16:48] = True
+        eng.zero_grad()
+        res = eng.forward(x, target, training=True, time_mask=tm, channel_mask=cm)
+        eng.backward()
+        assert torch.isfinite(eng.core.S.grad).all() and torch.isfinite(eng.head_grad).all()
+        outs.append((float(res["loss_sum"]), eng.core.S.grad.clone(), res["executed_blocks"]))
+    assert outs[0][2] == outs[1][2]
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
+    assert _rel(outs[0][1], outs[1][1]) < 1e-3
+    assert abs(outs[0][0] - outs[2][0]) > 1e-6 * abs(outs[0][0])
+    # random masks from the host generator: shapes and rates of the reference's compute_mask_indices calls
+    eng = FinetuneEngine(Cfg.tiny(), ft, 12, "cuda", precision="bf16", init=params)
+    res = eng.forward(x, target, training=True)
+    assert res["time_mask"].shape == (4, 400) and res["channel_mask"].shape == (4, 128)
+    assert 0.3 < res["time_mask"].mean() < 0.9 and 0.05 < res["channel_mask"].mean() < 0.7
+
+
+def test_dropin_finetune_model_and_criterion_against_the_oracle():
+    """wav2vec_ccas_finetune + finetunecriterion through the reference's call protocol (criterion(model, sample) ->
+    loss.backward() -> optimizer -> set_num_updates): logits / loss / counters / every parameter gradient against the
+    oracle (apply_mask off: the drop-in forward draws its masks from OS entropy like the reference)."""
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200.criterions import FinetuneCrossEntropyCriterion
+    from animal2vec_b200.wav2vec2 import Wav2VecCcasFinetune
+
+    cfg = O.tiny_config()
+    params = O.init_params(cfg, 0)
+    ft = Cfg.shipped_finetune(dropout=0.0, activation_dropout=0.0, attention_dropout=0.0, layerdrop=0.0, source_mixup=-1.0,
+                              average_top_k_layers=2, freeze_finetune_updates=0, apply_mask=False, load_ema=True)
+    state = {"model": {**{k: v.clone() for k, v in params.items()},
+                       "_ema": {k: v.clone() for k, v in O.make_teacher(params).items()}}}
+    model = Wav2VecCcasFinetune.build_model(ft, None, model_cfg=Cfg.no_randomness(Cfg.tiny()), state=state,
+                                            precision="fp32", metric_threshold=0.5)
+    sd = model.state_dict()
+    assert "w2v_encoder.proj.weight" in sd and "w2v_encoder.w2v_model.blocks.0.attn.qkv.weight" in sd
+    assert not any(".decoder." in k or "_ema" in k for k in sd)
+    gen = torch.Generator().manual_seed(9)
+    w = torch.randn(12, 128, generator=gen) * 0.2
+    bias = torch.randn(12, generator=gen) * 0.1
+    with torch.no_grad():
+        model.w2v_encoder.proj.weight.copy_(w.cuda())
+        model.w2v_encoder.proj.bias.copy_(bias.cuda())
+    b, n, t = 2, 16000, 400
+    x = F.layer_norm(torch.randn(b, n, generator=torch.Generator().manual_seed(6)), (n,))
+    target = (torch.rand(b, t, 12, generator=gen) < 0.15).float()
+    sample = {"id": torch.arange(b), "target": target.cuda(), "ntokens": b * t,
+              "net_input": {"source": x.cuda(), "target": target.cuda()}}
+    crit = FinetuneCrossEntropyCriterion(None, unique_labels=ft.unique_labels, report_accuracy=True, metric_threshold=0.5)
+    model.train()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-5)
+    opt.zero_grad()
+    loss, sample_size, log = crit(model, sample)
+    loss.backward()
+
+    student = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    wr, br = w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    oloss, ologits = O.finetune_loss(student, cfg, x, target, wr, br)
+    oloss.backward()
+    assert sample_size == b * t and abs(float(loss) - float(oloss)) <= 1e-3 * float(oloss)
+    tp, fp, tn, fn = O.confusion_counts(ologits.detach(), target, 0.5)
+    assert (log["finetune/tp"], log["finetune/fp"], log["finetune/tn"], log["finetune/fn"]) == (tp, fp, tn, fn)
+    named = dict(model.named_parameters())
+    assert _rel(named["w2v_encoder.proj.weight"].grad, wr.grad) < 3e-3
+    assert _rel(named["w2v_encoder.proj.bias"].grad, br.grad) < 3e-3
+    for k, p in student.items():
+        if ".decoder." in k:
+            continue
+        got = named["w2v_encoder.w2v_model." + k].grad
+        if p.grad is None:
+            assert float(got.abs().sum()) == 0.0, k
+        else:
+            assert _rel(got, p.grad) < 3e-3, (k, _rel(got, p.grad))
+    # second step after an outer zero_grad: gradients do not pile up
+    opt.step()
+    model.set_num_updates(1)
+    opt.zero_grad()
+    loss2, _, _ = crit(model, sample)
+    loss2.backward()
+    g2 = named["w2v_encoder.proj.weight"].grad.clone()
+    assert _rel(g2, wr.grad) < 0.05 and float(loss2) < float(loss)  # one small SGD step: nearly the same gradient, lower loss
+    red = crit.reduce_metrics([log])
+    assert abs(red["metrics/finetune/f1"] - round(tp * 200.0 / (2 * tp + fn + fp), 3)) < 1e-9

@@ -162,3 +162,44 @@ def test_oracle_finetune_head_focal_loss_and_confusion_match_reference():
     assert _rel(O.sigmoid_focal_loss(logits, target)[:, ::7], g["focal_none"]) < 1e-5
     assert abs(float(O.sigmoid_focal_loss(logits, target, reduction="sum")) - float(g["focal_sum"])) < 1e-5 * float(g["focal_sum"])
     assert list(O.confusion_counts(logits, target, float(g["metric_threshold"]))) == [int(v) for v in g["confusion"]]
+
+
+def test_oracle_finetune_training_step_matches_reference_golden():
+    """The finetune TRAINING step (masked features_only forward in train mode, top-k head, focal loss, autograd) of the
+    oracle against the reference's own forward + backward (tests/golden/make_golden_finetune.py)."""
+    g = _load("tiny_finetune.npz")
+    cfg = O.tiny_config()
+    params = O.init_params(cfg, 0)
+    b, n, t, classes = int(g["b"]), int(g["n"]), int(g["T"]), int(g["classes"])
+    x = F.layer_norm(torch.randn(b, n, generator=torch.Generator().manual_seed(int(g["seed_x"]))), (n,))
+    tm = torch.from_numpy(np.unpackbits(g["time_mask"], axis=1)[:, :t].astype(bool))
+    cm = torch.from_numpy(np.unpackbits(g["channel_mask"], axis=1)[:, : cfg.embed_dim].astype(bool))
+    gen = torch.Generator().manual_seed(int(g["head_seed"]))
+    w = (torch.randn(classes, cfg.embed_dim, generator=gen) * 0.2).requires_grad_(True)
+    bias = (torch.randn(classes, generator=gen) * 0.1).requires_grad_(True)
+    student = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    target = None
+    lrs = O.finetune_features(student, cfg, x, time_mask=tm, channel_mask=cm)
+    assert _rel(_sub(lrs[-1]), g["layer_last"]) < 1e-4
+    top = sum(lrs[-cfg.average_top_k_layers:]) / cfg.average_top_k_layers
+    logits = F.linear(top, w, bias)
+    target = (torch.rand(logits.shape, generator=gen) < 0.15).float()
+    loss = O.sigmoid_focal_loss(logits, target, reduction="sum")
+    loss2, logits2 = O.finetune_loss(student, cfg, x, target, w, bias, time_mask=tm, channel_mask=cm)
+    assert abs(float(loss) - float(loss2)) <= 1e-6 * abs(float(loss))
+    assert _rel(logits.detach()[:, ::7, :], g["logits"]) < 1e-4
+    assert abs(float(loss) - float(g["loss_sum"])) <= 1e-4 * float(g["loss_sum"])
+    loss.backward()
+    for k, nrm, head in zip([str(k) for k in g["grad_keys"]], g["grad_norms"], g["grad_heads"]):
+        gr = student[k].grad
+        assert abs(float(gr.double().norm()) - nrm) <= 1e-3 * nrm + 1e-9, (k, float(gr.norm()), nrm)
+        hv = gr.reshape(-1)[:8].numpy() if gr.numel() >= 8 else np.resize(gr.reshape(-1).numpy(), 8)
+        assert np.allclose(hv, head, rtol=2e-3, atol=1e-5 * nrm), k
+    assert abs(float(w.grad.double().norm()) - float(g["head_w_grad_norm"])) <= 1e-4 * float(g["head_w_grad_norm"])
+    assert np.allclose(bias.grad.numpy(), g["head_b_grad"], rtol=1e-4, atol=1e-5)
+    # frozen conv extractor, trainable projection (base.py:194-213)
+    assert bool(g["fe_grad_is_none"]) and student[O.ENC + "local_encoder.conv_layers.1.0.weight"].grad is None
+    pf = float(student[O.ENC + "project_features.2.weight"].grad.double().norm())
+    assert abs(pf - float(g["proj_feat_grad_norm"])) <= 1e-3 * float(g["proj_feat_grad_norm"])
+    tp, fp, tn, fn = O.confusion_counts(logits.detach(), target, float(g["metric_threshold"]))
+    assert [tp, fp, tn, fn] == [int(v) for v in g["confusion"][:4]]
