@@ -343,11 +343,38 @@ def alibi_bias(cfg: OracleConfig, scale: Tensor, pos: Tensor) -> Tensor:
     return -coef * dist[:, None]
 
 
-def attention(p: Dict[str, Tensor], pre: str, x: Tensor, bias: Tensor, heads: int) -> Tensor:
-    """AltAttention.forward (modules.py:368-410), dropout off."""
+class LazyAlibi:
+    """ALiBi bias evaluated per head / query chunk instead of as a (rows, H, L, L) tensor: the 48 kHz configuration
+    (T = 12 000) would need 9.2 GB per copy. Same values as :func:`alibi_bias`."""
+
+    def __init__(self, cfg: OracleConfig, scale: Tensor, pos: Tensor, chunk: int = 2048):
+        self.coef = (torch.tensor(alibi_slopes(cfg.num_heads), dtype=torch.float32) * scale.clamp_min(0).view(-1))
+        self.pos = pos.float()
+        self.chunk = chunk
+
+    def block(self, h: int, lo: int, hi: int) -> Tensor:
+        """(rows, hi - lo, L) bias of head h for query rows lo..hi."""
+        dist = (self.pos[:, lo:hi, None] - self.pos[:, None, :]).abs()
+        return -self.coef[h] * dist
+
+
+def attention(p: Dict[str, Tensor], pre: str, x: Tensor, bias, heads: int) -> Tensor:
+    """AltAttention.forward (modules.py:368-410), dropout off. ``bias``: dense (rows, H, L, L) tensor or LazyAlibi."""
     b, n, c = x.shape
     qkv = F.linear(x, p[pre + "qkv.weight"], p[pre + "qkv.bias"]).reshape(b, n, 3, heads, c // heads)
     q, k, v = qkv.permute(2, 0, 3, 1, 4)
+    if isinstance(bias, LazyAlibi):
+        q = q * (c // heads) ** -0.5
+        out = []
+        for h in range(heads):
+            rows = []
+            for lo in range(0, n, bias.chunk):
+                hi = min(n, lo + bias.chunk)
+                a = (q[:, h, lo:hi] @ k[:, h].transpose(-2, -1)).float() + bias.block(h, lo, hi)
+                rows.append(a.softmax(dim=-1) @ v[:, h])
+            out.append(torch.cat(rows, 1))
+        y = torch.stack(out, 2).reshape(b, n, c)
+        return F.linear(y, p[pre + "proj.weight"], p[pre + "proj.bias"])
     attn = (q * (c // heads) ** -0.5) @ k.transpose(-2, -1)
     attn = (attn.float() + bias).softmax(dim=-1)
     y = (attn @ v).transpose(1, 2).reshape(b, n, c)
@@ -509,7 +536,8 @@ def pretrain_forward(student: Dict[str, Tensor], teacher: Dict[str, Tensor], cfg
 
     with torch.no_grad():
         tpos = torch.arange(t).unsqueeze(0).expand(b, -1)
-        tbias = alibi_bias(cfg, teacher[ENC + "alibi_scale"], tpos)
+        tbias = (LazyAlibi(cfg, teacher[ENC + "alibi_scale"], tpos) if t > 4096
+                 else alibi_bias(cfg, teacher[ENC + "alibi_scale"], tpos))
         y = lf.detach() + positional_encoder(teacher, cfg, lf.detach())
         y = prenet(teacher, cfg, y, tbias)
         targets = []
