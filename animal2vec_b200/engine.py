@@ -547,9 +547,12 @@ class PretrainEngine:
 
     # ------------------------------------------------------------------------------------ forward
     def forward(self, source: torch.Tensor, ids=None, num_updates: int = 0, *, mask: Optional[np.ndarray] = None,
-                training: bool = True, need_grad: bool = True, taps: Optional[dict] = None) -> Dict[str, object]:
+                training: bool = True, need_grad: bool = True, taps: Optional[dict] = None,
+                fuse_loss_grad: bool = False) -> Dict[str, object]:
         """One pretraining forward. Returns loss_sum (device double scalar), sample_size, the logging statistics
-        and keeps what the backward needs in ``self.ctx``."""
+        and keeps what the backward needs in ``self.ctx``. ``fuse_loss_grad`` (bf16): the loss kernel also writes
+        d loss_sum / d pred over the prediction in the same pass; the following ``backward`` must then be called
+        without an upstream gradient scalar (the step driver's case)."""
         cfg, d, M = self.cfg, self.D, self.M
         L.require_device(source)
         if not (self.has_teacher and self.has_decoder):
@@ -625,8 +628,13 @@ class PretrainEngine:
 
         # ---- masked regression loss + collapse statistics
         scale = cfg.loss_scale if cfg.loss_scale is not None else 1.0 / math.sqrt(d)
-        loss_sum, stats = ops.d2v_loss_fwd(pred.view(R, T, d), y, mask_u8, M, float(scale) * float(cfg.d2v_loss))
-        c.y, c.mask_u8, c.scale = y, mask_u8, float(scale) * float(cfg.d2v_loss)
+        scale = float(scale) * float(cfg.d2v_loss)
+        c.loss_grad_fused = bool(fuse_loss_grad and save and not self.fp32 and taps is None and d % 256 == 0)
+        if c.loss_grad_fused:
+            loss_sum, stats = ops.d2v_loss_fused(pred.view(R, T, d), y, mask_u8, M, scale, 2.0 * scale)
+        else:
+            loss_sum, stats = ops.d2v_loss_fwd(pred.view(R, T, d), y, mask_u8, M, scale)
+        c.y, c.mask_u8, c.scale = y, mask_u8, scale
         c.lf = lf
         self.ctx = c if save else None
         return {"loss_sum": loss_sum, "colstats": stats, "sample_size": n_masked, "masked_pct": 1.0 - tk / T,
@@ -735,7 +743,12 @@ class PretrainEngine:
         W, G, d = self.WS, self.G, self.D
         mi, B, T, tk, R, M = c.mi, c.B, c.T, c.tk, c.R, self.M
         dc = self.dec
-        dpred = ops.d2v_loss_bwd(c.pred.view(R, T, d), c.y, c.mask_u8, M, c.scale, grad_scale).view(R * T, d)
+        if c.loss_grad_fused:
+            if grad_scale is not None:
+                raise RuntimeError("forward(fuse_loss_grad=True) already wrote the gradient for an upstream scalar of 1")
+            dpred = c.pred.view(R * T, d)  # overwritten in place by the fused loss kernel
+        else:
+            dpred = ops.d2v_loss_bwd(c.pred.view(R, T, d), c.y, c.mask_u8, M, c.scale, grad_scale).view(R * T, d)
         # decoder projection
         n = ENC + "decoder.proj.weight"
         ops.colsum(dpred, G(ENC + "decoder.proj.bias"))

@@ -321,6 +321,19 @@ def d2v_loss_fwd(pred, y, mask_u8, clones, scale):
     return acc[0:1], acc[1:].view(4, d_)
 
 
+def d2v_loss_fused(pred, y, mask_u8, clones, scale, grad_coef: Optional[float]):
+    """One pass: (loss_sum, colstats) and -- when ``grad_coef`` is given -- the gradient grad_coef * (pred - y) on masked
+    rows, zeros elsewhere, written IN PLACE over ``pred`` (bf16, D % 256 == 0)."""
+    r, t, d_ = pred.shape
+    assert pred.is_contiguous() and pred.dtype == torch.bfloat16 and y.is_contiguous() and y.dtype == torch.float32
+    acc = torch.zeros(1 + 4 * d_, device=pred.device, dtype=torch.float64)
+    _call("a2v_d2v_loss_fused", pred, L.dtype_code(pred), _p(pred), _p(y), _p(mask_u8),
+          _p(pred) if grad_coef is not None else None, C.c_int64(r), t, clones, d_, C.c_float(scale),
+          C.c_float(grad_coef if grad_coef is not None else 0.0), C.c_void_p(acc.data_ptr()),
+          C.c_void_p(acc.data_ptr() + 8))
+    return acc[0:1], acc[1:].view(4, d_)
+
+
 def d2v_loss_bwd(pred, y, mask_u8, clones, scale, grad_out: Optional[torch.Tensor]):
     r, t, d_ = pred.shape
     dpred = torch.empty_like(pred)

@@ -139,7 +139,7 @@ class PretrainTrainer:
         sample_size = 0
         res = None
         for i, (source, ids) in enumerate(micro_batches):
-            res = e.forward(source, ids, self.num_updates, training=True)
+            res = e.forward(source, ids, self.num_updates, training=True, fuse_loss_grad=True)
             last = i == n_mb - 1
             e.backward(None, training=True, block_done=self._block_done if last else None)
             self.stats[0:1] += res["loss_sum"]

@@ -223,6 +223,13 @@ int a2v_d2v_loss_fwd(int dtype, const void* pred, const float* y, const uint8_t*
                      int D, float scale, double* loss_sum, double* colstats, a2v_stream_t stream);
 int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t* mask, void* dpred, int64_t R, int T,
                      int clones, int D, float scale, const float* grad_out_dev, a2v_stream_t stream);
+/* Forward and backward of the masked regression loss in ONE pass (bf16, D % 256 == 0): loss_sum / colstats as in
+ * a2v_d2v_loss_fwd, and dpred = grad_coef * (pred - y) on masked rows, 0 elsewhere (grad_coef = 2 * scale * upstream
+ * gradient). dpred may alias pred (the prediction is not needed afterwards: nn/data2vec2.py:850-862 only feeds the
+ * loss) or be NULL (statistics only). The target row of a frame is read once for all `clones` clones. */
+int a2v_d2v_loss_fused(int dtype, const void* pred, const float* y, const uint8_t* mask, void* dpred, int64_t R, int T,
+                       int clones, int D, float scale, float grad_coef, double* loss_sum, double* colstats,
+                       a2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Utilities.

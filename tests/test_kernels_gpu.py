@@ -339,6 +339,35 @@ def test_mask_index_and_gathers():
 
 
 # --------------------------------------------------------------------------------------- targets / loss
+@pytest.mark.parametrize("b,m,t,d", [(2, 12, 333, 1024), (3, 5, 100, 256), (1, 7, 2000, 512)])
+def test_loss_fused_forward_backward_in_place(b, m, t, d):
+    """a2v_d2v_loss_fused (bf16): loss, the four column statistics and the in-place gradient against torch and against
+    the separate forward / backward kernels; wide target kernels against F.instance_norm."""
+    from animal2vec_b200 import ops
+
+    r = b * m
+    pred = torch.randn(r, t, d, device="cuda", generator=_g(1)).bfloat16()
+    y = torch.randn(b, t, d, device="cuda", generator=_g(2))
+    mask = (torch.rand(r, t, device="cuda", generator=_g(3)) < 0.9).to(torch.uint8)
+    scale = d ** -0.5
+    l0, st0 = ops.d2v_loss_fwd(pred, y, mask, m, scale)  # dispatches to the fused kernel without gradient
+    g0 = ops.d2v_loss_bwd(pred, y, mask, m, scale, None)
+    mb = mask.bool()
+    yc = y.repeat_interleave(m, 0)
+    xs, ys = pred.float()[mb], yc[mb]
+    ref_loss = ((xs - ys) ** 2).sum().double() * scale
+    assert abs(float(l0) - float(ref_loss)) <= 1e-5 * float(ref_loss)
+    for k, v in enumerate((xs.sum(0), (xs * xs).sum(0), ys.sum(0), (ys * ys).sum(0))):
+        assert _rel(st0[k], v) < 1e-5, k
+    work = pred.clone()
+    l1, st1 = ops.d2v_loss_fused(work, y, mask, m, scale, 2.0 * scale)
+    assert abs(float(l1) - float(l0)) <= 1e-9 * abs(float(l0)) + 1e-9 and _rel(st1, st0) < 1e-7
+    ref_g = (2 * scale * (pred.float() - yc)) * mb.unsqueeze(-1)
+    assert _rel(work, ref_g) < 4e-3 and _rel(work, g0) < 1e-6
+    assert float(work[~mb].abs().sum()) == 0.0
+
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_targets_and_loss(dtype):
     from animal2vec_b200 import ops

@@ -188,3 +188,11 @@ def test_large_config_bf16_gradients_match_the_cpu_oracle():
     flat_g = torch.cat([eng.S.gview(k).reshape(-1).double().cpu() for k in eng.S.names])
     cos = float((flat_o * flat_g).sum() / (flat_o.norm() * flat_g.norm()))
     assert cos > 0.9995, cos
+    # the step driver's variant: loss + loss gradient in one pass over the predictions (a2v_d2v_loss_fused)
+    g_sep = eng.S.grad.clone()
+    eng.zero_grad()
+    res2 = eng.forward(x.cuda(), ids, 2, fuse_loss_grad=True)
+    assert abs(float(res2["loss_sum"].item()) - loss) <= 1e-6 * abs(loss)
+    assert _rel(res2["colstats"], res["colstats"]) < 1e-6
+    eng.backward()
+    assert _rel(eng.S.grad, g_sep) < 2e-3, _rel(eng.S.grad, g_sep)  # split-K / atomic ordering noise only
