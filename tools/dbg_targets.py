@@ -1,0 +1,27 @@
+"""Target precision probe: bf16 engine targets vs the CPU oracle with / without centred storage of the teacher FFN outputs."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.nn.functional as F
+from animal2vec_b200 import config as Cfg
+from animal2vec_b200.engine import PretrainEngine
+from oracle import a2v_oracle as O
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+ocfg = O.large_config(); params = O.init_params(ocfg, 0); n = 80000
+x = F.layer_norm(torch.randn(1, n, generator=torch.Generator().manual_seed(3)), (n,)); ids = torch.arange(1) + 11
+otaps = {}
+with torch.no_grad():
+    O.pretrain_forward(params, O.make_teacher(params), ocfg, x, ids, 2, taps=otaps)
+for prec in ("bf16", "fp32"):
+    for center in ((True, False) if prec == "bf16" else (False,)):
+        eng = PretrainEngine(Cfg.no_randomness(Cfg.shipped_large()), "cuda", precision=prec, init=params)
+        eng.center_targets = center
+        taps = {}
+        eng.forward(x.cuda(), ids, 2, taps=taps, need_grad=False)
+        print(prec, "center", center, "targets rel", rel(taps["targets"], otaps["targets"]),
+              "local_features rel", rel(taps["local_features"].float(), otaps["local_features"]))
+        del eng, taps
+        torch.cuda.empty_cache()
