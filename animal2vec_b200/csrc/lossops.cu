@@ -292,23 +292,6 @@ __global__ void __launch_bounds__(256) d2v_loss_fused_bf16_kernel(const bf16* pr
     }
 }
 
-// shift[l][c] += mean_b stats[l][b][c].mean ;  bias_out[l][c] = bias_l[c] - shift[l][c].   grid (ceil(D/256), K)
-__global__ void __launch_bounds__(256) target_shift_update_kernel(const float2* __restrict__ stats, int B, int D,
-                                                                  float* __restrict__ shift,
-                                                                  const float* const* __restrict__ bias_ptrs,
-                                                                  float* __restrict__ bias_out) {
-    const int c = blockIdx.x * 256 + threadIdx.x, l = blockIdx.y;
-    if (c >= D) return;
-    float s = shift[(long long)l * D + c];
-    if (stats != nullptr) {
-        float m = 0.f;
-        for (int b = 0; b < B; ++b) m += stats[((long long)l * B + b) * D + c].x;
-        s += m / (float)B;
-        shift[(long long)l * D + c] = s;
-    }
-    bias_out[(long long)l * D + c] = bias_ptrs[l][c] - s;
-}
-
 // bf16 instance-norm statistics: 256-column slab per block, four frames in flight per warp. grid (D/256, B, K)
 __global__ void __launch_bounds__(256) target_stats_bf16_wide_kernel(const void* const* __restrict__ layers,
                                                                      float2* __restrict__ stats, int B, int T_, int D,
@@ -431,15 +414,6 @@ extern "C" int a2v_target_stats(int dtype, const void* const* layers_dev, int K,
     else
         target_stats_kernel<bf16><<<grid, 256, 0, st>>>(layers_dev, (float2*)stats, B, T, D, eps);
     return a2v_check_launch("target_stats");
-}
-
-extern "C" int a2v_target_shift_update(const float* stats, int K, int B, int D, float* shift, const void* const* bias_ptrs,
-                                       float* bias_out, a2v_stream_t stream) {
-    A2V_REQUIRE(shift && bias_ptrs && bias_out && K > 0 && D > 0 && (stats == nullptr || B > 0),
-                "target_shift_update: bad arguments");
-    target_shift_update_kernel<<<dim3(ceil_div(D, 256), K), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float2*>(stats), B, D, shift, reinterpret_cast<const float* const*>(bias_ptrs), bias_out);
-    return a2v_check_launch("target_shift_update");
 }
 
 extern "C" int a2v_target_apply(int dtype, const void* const* layers_dev, int K, int B, int T, int D,

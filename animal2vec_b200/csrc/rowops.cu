@@ -46,7 +46,6 @@ struct RowLnParams {
     float* dbeta;
     float* dact_alpha;
     float* dact_beta;
-    const float* b_offset;  // forward, residual fast path only: y = LN(a + (b + b_offset))
 };
 
 __device__ __forceinline__ int param_index(int c, int gw, int gr) { return (c / gw) * gr + (c % gw); }
@@ -872,8 +871,8 @@ __global__ void __launch_bounds__(256, 2) resln_fwd_kernel(const RowLnParams p, 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long warp0 = (long long)blockIdx.x * ROWLN_WARPS + warp;
     const long long nwarps = (long long)gridDim.x * ROWLN_WARPS;
-    float* tab = reinterpret_cast<float*>(smem_raw);  // [gamma | beta | b_offset] x C
-    unsigned char* rings = smem_raw + 3 * C * sizeof(float);
+    float* tab = reinterpret_cast<float*>(smem_raw);  // [gamma | beta] x C
+    unsigned char* rings = smem_raw + 2 * C * sizeof(float);
     unsigned char* ring = rings + (size_t)warp * stages * NTENS * row_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(rings + (size_t)ROWLN_WARPS * stages * NTENS * row_bytes) + warp * FAST_STAGES_MAX;
     const unsigned char* src[NTENS];
@@ -882,11 +881,9 @@ __global__ void __launch_bounds__(256, 2) resln_fwd_kernel(const RowLnParams p, 
     int off[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) off[i] = (lane + 32 * i) * 16;
-    const bool has_off = HAS_B && p.b_offset != nullptr;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         tab[c] = p.gamma[c];
         tab[C + c] = p.beta != nullptr ? p.beta[c] : 0.f;
-        tab[2 * C + c] = has_off ? p.b_offset[c] : 0.f;
     }
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
@@ -922,12 +919,6 @@ __global__ void __launch_bounds__(256, 2) resln_fwd_kernel(const RowLnParams p, 
             if (HAS_B) {
                 float t[8];
                 unpack8(vb[i], t);
-                if (has_off) {  // b was stored centred: restore the per-channel offset
-                    const float4 o0 = *reinterpret_cast<const float4*>(tab + 2 * C + (off[i] >> 1));
-                    const float4 o1 = *reinterpret_cast<const float4*>(tab + 2 * C + (off[i] >> 1) + 4);
-                    t[0] += o0.x; t[1] += o0.y; t[2] += o0.z; t[3] += o0.w;
-                    t[4] += o1.x; t[5] += o1.y; t[6] += o1.z; t[7] += o1.w;
-                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (DROP) t[j] = ((keep >> (8 * i + j)) & 1u) ? t[j] * keep_b : 0.f;
@@ -1110,7 +1101,7 @@ static int launch_resln_fast(const RowLnParams& p, bool bwd, float* dbias_b, cud
     const bool has_b = p.b != nullptr, drop = p.drop_b > 0.f;
     const int ntens = bwd ? (has_b ? 3 : 2) : (has_b ? 2 : 1);
     const int row_bytes = p.C * 2;
-    const size_t fixed = (bwd ? 0 : (size_t)3 * p.C * sizeof(float)) + (size_t)ROWLN_WARPS * FAST_STAGES_MAX * 8;
+    const size_t fixed = (bwd ? 0 : (size_t)2 * p.C * sizeof(float)) + (size_t)ROWLN_WARPS * FAST_STAGES_MAX * 8;
     const size_t per_stage = (size_t)ROWLN_WARPS * ntens * row_bytes;
     const size_t budget = bwd ? 200 * 1024 : 110 * 1024;
     int stages = (int)((budget - fixed) / per_stage);
@@ -1299,7 +1290,6 @@ static RowLnParams to_params(const a2v_rowln_desc* d) {
     p.drop_b = d->drop_b; p.seed_b = d->seed_b; p.drop_out = d->drop_out; p.seed_out = d->seed_out;
     p.dy = d->dy; p.da = d->da; p.db = d->db;
     p.dgamma = d->dgamma; p.dbeta = d->dbeta; p.dact_alpha = d->dact_alpha; p.dact_beta = d->dact_beta;
-    p.b_offset = d->b_offset;
     return p;
 }
 
@@ -1314,13 +1304,6 @@ extern "C" int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream) {
     if (d->rows == 0) return A2V_OK;
     RowLnParams p = to_params(d);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (d->b_offset != nullptr) {  // only the bf16 residual-norm kernel knows the centred-b convention
-        A2V_REQUIRE(d->dtype == A2V_BF16 && d->b != nullptr, "rowln_fwd: b_offset needs bf16 and b");
-        rc = launch_resln_fast(p, false, nullptr, st);
-        A2V_REQUIRE(rc >= 0, "rowln_fwd: b_offset is supported by the residual LayerNorm kernel only (affine, no "
-                             "activation, C in {512, 768, 1024}, 16-byte aligned operands)");
-        return rc;
-    }
     if (d->dtype == A2V_BF16) {
         rc = launch_rowln_fast(p, false, st);
         if (rc >= 0) return rc;

@@ -137,10 +137,6 @@ class PretrainEngine:
         self.kernel_launches = 0
         self.has_teacher = True
         self.has_decoder = True
-        # bf16: the teacher's target layers are stored centred (see _teacher_targets)
-        self.center_targets = True
-        self._t_shift = self._t_bias_c = None
-        self._t_shift_ready = False
 
     # ------------------------------------------------------------------------------------ support matrix
     @staticmethod
@@ -201,14 +197,12 @@ class PretrainEngine:
         self.E.data.copy_(self.S.data[: self.E.total])
         self._teacher_dirty = True
         self._t16_valid = False
-        self._t_shift_ready = False  # new teacher weights: recalibrate the centred target storage
 
     def load_teacher(self, tensors: Dict[str, torch.Tensor]) -> None:
         for k in self.E.names:
             self.E.view(k).copy_(tensors[k].to(self.device, torch.float32).reshape(self.E.shapes[k]))
         self._teacher_dirty = True
         self._t16_valid = False
-        self._t_shift_ready = False
 
     def drop_teacher(self) -> None:
         """remove_pretraining_modules (nn/data2vec2.py:1125-1127): the EMA teacher and its fp32 shadow are released."""
@@ -486,11 +480,8 @@ class PretrainEngine:
             x = act
         return x
 
-    def _block_forward(self, W: _Weights, pre: str, x, rows, seq, pos, train: bool, save: Optional[list], site: int,
-                       center=None):
-        """AltBlock.forward, post-LN branch (modules.py:328-337) with AltAttention (:368-410) and timm Mlp.
-        ``center`` = (fc2 bias minus shift, shift), both (D,) fp32: the FFN output ``t`` is produced and returned
-        CENTRED (t - shift) and the second norm adds the shift back (teacher target layers, see _teacher_targets)."""
+    def _block_forward(self, W: _Weights, pre: str, x, rows, seq, pos, train: bool, save: Optional[list], site: int):
+        """AltBlock.forward, post-LN branch (modules.py:328-337) with AltAttention (:368-410) and timm Mlp."""
         cfg, d = self.cfg, self.D
         f = W.f32
         qkv = self.lin(x, W, pre + "attn.qkv.weight", bias=f[pre + "attn.qkv.bias"])
@@ -509,11 +500,10 @@ class PretrainEngine:
         s_mlp = self._seed(site + 3)
         if p_mlp > 0:
             h = ops.row_gather(h, self._arange(rows * seq), rows * seq, drop_p=p_mlp, drop_seed=s_mlp)
-        t = self.lin(h, W, pre + "mlp.fc2.weight", bias=f[pre + "mlp.fc2.bias"] if center is None else center[0])
+        t = self.lin(h, W, pre + "mlp.fc2.weight", bias=f[pre + "mlp.fc2.bias"])
         c2 = ops.RowLnCfg(d, cfg.norm_eps, drop_b=cfg.post_mlp_drop)
         x2, m2, r2 = ops.rowln_fwd(c2, x1, t, f[pre + "norm2.weight"], f[pre + "norm2.bias"], seed_b=s2,
-                                   training=train, save_stats=save is not None,
-                                   b_offset=None if center is None else center[1])
+                                   training=train, save_stats=save is not None)
         if save is not None:
             save.append(SimpleNamespace(pre=pre, x=x, qkv=qkv, ao=ao, lse=lse, pr=pr, x1=x1, m1=m1, r1=r1, u=u, h=h,
                                         t=t, m2=m2, r2=r2, s_att=s_att, s1=s1, s2=s2, p_att=p_att, c1=c1, c2=c2,
@@ -521,9 +511,8 @@ class PretrainEngine:
         return x2, t
 
     def _encoder_forward(self, W: _Weights, x, rows, seq, pos, train, save: Optional[list], targets: Optional[list],
-                         c: Optional[SimpleNamespace], center=None):
-        """BlockEncoder (modules.py:83-108: LN -> dropout -> prenet blocks) followed by the main blocks.
-        ``center`` = (bias_c (K, D), shift (K, D)): the last K blocks emit centred FFN outputs."""
+                         c: Optional[SimpleNamespace]):
+        """BlockEncoder (modules.py:83-108: LN -> dropout -> prenet blocks) followed by the main blocks."""
         cfg = self.cfg
         cn = ops.RowLnCfg(self.D, cfg.norm_eps, drop_out=self.a.prenet_dropout)
         s_pre = self._seed(1)
@@ -533,58 +522,11 @@ class PretrainEngine:
         if save is not None:
             c.prenorm = SimpleNamespace(x=x, m=m, r=r, cfg=cn, seed=s_pre)
         x = xn
-        nb = len(self.block_prefixes)
         for j, pre in enumerate(self.block_prefixes):
-            ck = None
-            if center is not None and j >= nb - center[0].shape[0]:
-                k = j - (nb - center[0].shape[0])
-                ck = (center[0][k], center[1][k])
-            x, t = self._block_forward(W, pre, x, rows, seq, pos, train, save, 16 + 4 * j, center=ck)
+            x, t = self._block_forward(W, pre, x, rows, seq, pos, train, save, 16 + 4 * j)
             if targets is not None and j >= self.a.prenet_depth:
                 targets.append(t.view(rows, seq, self.D))
         return x
-
-    # ------------------------------------------------------------------------------------ teacher targets
-    def _teacher_targets(self, lf: torch.Tensor) -> torch.Tensor:
-        """Teacher forward (nn/data2vec2.py:779-844, no grad, eval mode) + make_targets (:1023-1066).
-
-        bf16 mode stores the top-K FFN outputs CENTRED: at the reference's own initialisation their per-channel mean is
-        7..200 temporal standard deviations away from zero, so bf16 rounding of the raw values, expressed in the units
-        F.instance_norm divides by, costs 4.5 % of the target (11 % at 48 kHz); rounding t - shift_c with a per-channel
-        shift tracked from the previous step's instance-norm means costs 0.2 % (fp16, the reference's storage: 0.6 %).
-        Instance norm is shift invariant, so the targets need no correction; the block's second LayerNorm gets the
-        shift back through ``b_offset``. The first forward calibrates the shift with one extra teacher pass."""
-        cfg, d = self.cfg, self.D
-        B, T = lf.shape[0], lf.shape[1]
-        K = min(cfg.average_top_k_layers, cfg.depth)
-        y_pos = self._posconv_forward(self.WT, lf, None)
-        ty = self._add(y_pos.view(B * T, d), lf.view(B * T, d))
-        del y_pos
-        center = None
-        use_center = self.center_targets and not self.fp32 and d % 256 == 0 and 512 <= d <= 1024
-        if use_center:
-            if self._t_shift is None:
-                self._t_shift = torch.zeros(K, d, device=self.device, dtype=torch.float32)
-                self._t_bias_c = torch.empty(K, d, device=self.device, dtype=torch.float32)
-                self._t_shift_ready = False
-            names = [pre + "mlp.fc2.bias" for pre in self.block_prefixes[-K:]]
-            ptrs = ops.h2d_async(torch.tensor([self.WT.f32[n].data_ptr() for n in names], dtype=torch.int64), self.device)
-            center = (self._t_bias_c, self._t_shift)
-            passes = 1 if self._t_shift_ready else 2
-        else:
-            passes = 1
-        y = None
-        for it in range(passes):
-            if use_center:
-                ops.target_shift_update(None, self._t_shift, ptrs, self._t_bias_c)  # bias_c = (EMA-updated) bias - shift
-            targets: List[torch.Tensor] = []
-            self._encoder_forward(self.WT, ty, B, T, None, False, None, targets, None, center=center)
-            y, stats = ops.make_targets(targets[-K:], 1e-5, return_stats=True)
-            del targets
-            if use_center:
-                ops.target_shift_update(stats, self._t_shift, ptrs, self._t_bias_c)
-                self._t_shift_ready = True
-        return y
 
     def _decoder_forward(self, W: _Weights, x: torch.Tensor, save: Optional[list]) -> torch.Tensor:
         """Decoder1d.forward (modules.py:179-192) on the group-padded layout; residual rule of :124-134."""
@@ -674,7 +616,13 @@ class PretrainEngine:
             taps["decoder_out"] = pred
 
         # ---- teacher (no grad, eval mode): full-length positional conv + encoder, top-K FFN targets
-        y = self._teacher_targets(lf)
+        y_pos = self._posconv_forward(self.WT, lf, None)
+        ty = ops.row_gather(lf2, self._arange(B * T), B * T, add=y_pos.view(B * T, d), out_shape=(B * T, d))
+        del y_pos
+        targets: List[torch.Tensor] = []
+        self._encoder_forward(self.WT, ty, B, T, None, False, None, targets, None)
+        y = ops.make_targets(targets[-cfg.average_top_k_layers:], 1e-5)
+        del targets
         if taps is not None:
             taps["targets"] = y
 

@@ -43,7 +43,6 @@ class RowLnDesc(C.Structure):
         ("dact_alpha", C.c_void_p),
         ("dact_beta", C.c_void_p),
         ("dbias_b", C.c_void_p),
-        ("b_offset", C.c_void_p),
     ]
 
 
@@ -157,7 +156,7 @@ def _rowln_desc(cfg: RowLnCfg, a, b, gamma, beta, act_alpha, act_beta, post, y, 
 
 
 def rowln_fwd(cfg: RowLnCfg, a, b=None, gamma=None, beta=None, act_alpha=None, act_beta=None, post=None,
-              seed_b=0, seed_out=0, training=True, save_stats=True, b_offset=None):
+              seed_b=0, seed_out=0, training=True, save_stats=True):
     assert a.is_contiguous() and a.shape[-1] == cfg.channels
     for t in (b, post):
         assert t is None or (t.is_contiguous() and t.shape == a.shape and t.dtype == a.dtype)
@@ -166,9 +165,6 @@ def rowln_fwd(cfg: RowLnCfg, a, b=None, gamma=None, beta=None, act_alpha=None, a
     mean = torch.empty(rows, device=a.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty(rows, device=a.device, dtype=torch.float32) if save_stats else None
     d = _rowln_desc(cfg, a, b, gamma, beta, act_alpha, act_beta, post, y, mean, rstd, seed_b, seed_out, training)
-    if b_offset is not None:
-        assert b_offset.dtype == torch.float32 and b_offset.numel() == cfg.channels and b_offset.is_contiguous()
-        d.b_offset = _p(b_offset)
     _call("a2v_rowln_fwd", a, C.byref(d))
     return y, mean, rstd
 
@@ -301,7 +297,7 @@ def clone_sum_bwd(d_masked, d_unmasked, restore_src, b, t, clones, d_):
 
 
 # ----------------------------------------------------------------------------- targets / loss
-def make_targets(layers: Sequence[torch.Tensor], eps: float = 1e-5, return_stats: bool = False):
+def make_targets(layers: Sequence[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
     k = len(layers)
     b, t, d_ = layers[0].shape
     for x in layers:
@@ -313,16 +309,7 @@ def make_targets(layers: Sequence[torch.Tensor], eps: float = 1e-5, return_stats
     code = L.dtype_code(layers[0])
     _call("a2v_target_stats", layers[0], code, _p(ptrs), k, b, t, d_, C.c_float(eps), _p(stats))
     _call("a2v_target_apply", layers[0], code, _p(ptrs), k, b, t, d_, _p(stats), _p(y))
-    return (y, stats) if return_stats else y
-
-
-def target_shift_update(stats: Optional[torch.Tensor], shift: torch.Tensor, bias_ptrs: torch.Tensor,
-                        bias_out: torch.Tensor) -> None:
-    """shift (K, D) += clip-mean of the instance-norm means in ``stats`` (K, B, D, 2) (skipped when None);
-    bias_out (K, D) = bias_l - shift_l for the K device bias pointers in ``bias_ptrs``."""
-    k, d_ = shift.shape
-    b = stats.shape[1] if stats is not None else 0
-    _call("a2v_target_shift_update", shift, _p(stats), k, b, d_, _p(shift), _p(bias_ptrs), _p(bias_out))
+    return y
 
 
 def d2v_loss_fwd(pred, y, mask_u8, clones, scale):

@@ -177,12 +177,6 @@ typedef struct {
     float* dact_alpha;
     float* dact_beta;
     float* dbias_b;            /* optional: += column sums of db (the bias gradient of the Linear that produced b) */
-    /* forward, optional (bf16 residual norms, C in {512, 768, 1024}): per-channel fp32 vector added to b before the sum,
-     * y = LN(a + (b + b_offset)). Lets a producer store b CENTERED (b - b_offset): the EMA teacher's FFN outputs have
-     * |channel mean| / temporal std of 7..200 at the reference's own initialisation, so their bf16 rounding error, measured
-     * in units of the temporal std that F.instance_norm divides by (nn/data2vec2.py:1041-1047), is 4.5 % of the target;
-     * centred storage brings it to 0.2 % (the reference's fp16 storage: 0.6 %). */
-    const float* b_offset;
 } a2v_rowln_desc;
 
 int a2v_rowln_fwd(const a2v_rowln_desc* d, a2v_stream_t stream);
@@ -225,11 +219,6 @@ int a2v_target_stats(int dtype, const void* const* layers_dev, int K, int B, int
                      a2v_stream_t stream);
 int a2v_target_apply(int dtype, const void* const* layers_dev, int K, int B, int T, int D, const float* stats,
                      float* y, a2v_stream_t stream);
-/* Centred storage of the teacher's FFN outputs (see a2v_rowln_desc.b_offset): shift[l][c] += mean over the B clips of the
- * instance-norm means stats[l][b][c] (which are means of the CENTRED outputs), and the bias each layer's fc2 GEMM must
- * use next step, bias_out[l][c] = bias_l[c] - shift[l][c] (bias_ptrs: DEVICE table of K fp32 bias vectors). */
-int a2v_target_shift_update(const float* stats, int K, int B, int D, float* shift, const void* const* bias_ptrs,
-                            float* bias_out, a2v_stream_t stream);
 int a2v_d2v_loss_fwd(int dtype, const void* pred, const float* y, const uint8_t* mask, int64_t R, int T, int clones,
                      int D, float scale, double* loss_sum, double* colstats, a2v_stream_t stream);
 int a2v_d2v_loss_bwd(int dtype, const void* pred, const float* y, const uint8_t* mask, void* dpred, int64_t R, int T,

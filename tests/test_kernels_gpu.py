@@ -338,37 +338,6 @@ def test_mask_index_and_gathers():
     assert ops.mask_index(mask, tk + 1, m).err.item() != 0
 
 
-@pytest.mark.parametrize("c", [512, 1024])
-def test_rowln_residual_centred_b_offset_and_shift_update(c):
-    """y = LN(a + (b + b_offset)): a producer may store b centred (teacher target layers). Also the shift bookkeeping
-    kernel: shift += clip-mean of the instance-norm means, bias_out = bias - shift."""
-    from animal2vec_b200 import ops
-
-    rows = 3001
-    a = torch.randn(rows, c, device="cuda", generator=_g(1)).bfloat16()
-    off = torch.randn(c, device="cuda", generator=_g(2)) * 20  # channel means far from zero
-    dev = torch.randn(rows, c, device="cuda", generator=_g(3)) * 0.3
-    gamma = torch.rand(c, device="cuda", generator=_g(4)) + 0.5
-    beta = torch.randn(c, device="cuda", generator=_g(5))
-    cfg = ops.RowLnCfg(c, 1e-5)
-    ref = F.layer_norm(a.float() + dev + off, (c,), gamma, beta, 1e-5)
-    y_c, _, _ = ops.rowln_fwd(cfg, a, dev.bfloat16(), gamma, beta, b_offset=off)          # b stored centred
-    y_r, _, _ = ops.rowln_fwd(cfg, a, (dev + off).bfloat16(), gamma, beta)               # b stored raw
-    assert _rel(y_c, ref) < 6e-3
-    assert _rel(y_c, ref) <= _rel(y_r, ref) * 1.05  # never worse than raw storage
-    k, b = 3, 4
-    stats = torch.randn(k, b, c, 2, device="cuda", generator=_g(6))
-    shift = torch.randn(k, c, device="cuda", generator=_g(7))
-    biases = [torch.randn(c, device="cuda", generator=_g(8 + i)) for i in range(k)]
-    ptrs = torch.tensor([x.data_ptr() for x in biases], dtype=torch.int64, device="cuda")
-    out = torch.empty(k, c, device="cuda")
-    want_shift = shift + stats[..., 0].mean(1)
-    ops.target_shift_update(stats, shift, ptrs, out)
-    assert _rel(shift, want_shift) < 1e-6 and _rel(out, torch.stack(biases) - want_shift) < 1e-6
-    ops.target_shift_update(None, shift, ptrs, out)  # bias refresh only
-    assert _rel(shift, want_shift) < 1e-6 and _rel(out, torch.stack(biases) - want_shift) < 1e-6
-
-
 # --------------------------------------------------------------------------------------- targets / loss
 @pytest.mark.parametrize("b,m,t,d", [(2, 12, 333, 1024), (3, 5, 100, 256), (1, 7, 2000, 512)])
 def test_loss_fused_forward_backward_in_place(b, m, t, d):

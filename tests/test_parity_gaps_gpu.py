@@ -163,29 +163,14 @@ def test_large_config_bf16_gradients_match_the_cpu_oracle():
     torch.set_num_threads(max(1, torch.get_num_threads()))
     student = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     teacher = O.make_teacher(params)
-    otaps = {}
-    ores = O.pretrain_forward(student, teacher, ocfg, x, ids, 2, taps=otaps)
+    ores = O.pretrain_forward(student, teacher, ocfg, x, ids, 2)
     oloss = ores["losses"]["AUDIO_regression"].sum()
     oloss.backward()
 
     eng = PretrainEngine(Cfg.no_randomness(Cfg.shipped_large()), "cuda", precision="bf16", init=params)
     eng.zero_grad()
-    taps = {}
-    res = eng.forward(x.cuda(), ids, 2, taps=taps)
-    assert np.array_equal(res["mask"], ores["mask"].numpy())
-    # regression targets: the teacher's FFN outputs are stored CENTRED in bf16 (engine._teacher_targets); stored raw,
-    # their rounding costs 4.5 % of the instance-normed target at this initialisation (|channel mean| >> temporal std)
-    e_t = _rel(taps["targets"], otaps["targets"])
-    assert e_t < 1.5e-2, e_t
-    eng.center_targets = False
-    t_raw = {}
-    eng.forward(x.cuda(), ids, 2, taps=t_raw, need_grad=False)
-    eng.center_targets = True
-    e_raw = _rel(t_raw["targets"], otaps["targets"])
-    assert e_raw > 2 * e_t, (e_raw, e_t)
-    del taps, t_raw
-    eng.zero_grad()
     res = eng.forward(x.cuda(), ids, 2)
+    assert np.array_equal(res["mask"], ores["mask"].numpy())
     loss = float(res["loss_sum"].item())
     assert abs(loss - float(oloss.detach())) / abs(float(oloss.detach())) < 1e-2
     eng.backward()
