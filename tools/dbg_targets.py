@@ -1,4 +1,6 @@
-"""Target precision probe: bf16 engine targets vs the CPU oracle with / without centred storage of the teacher FFN outputs."""
+"""Target precision probe: engine targets (bf16 / fp32 mode) vs the CPU oracle on the large config at the reference's
+initialisation. Measured on B200 (round 2): bf16 0.14, fp32 2.6e-4; storing the FFN outputs centred in bf16 only moved it
+to 0.13 (the noise comes from the bf16 activations upstream, not from the final rounding), so that variant was dropped."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
@@ -16,9 +18,8 @@ otaps = {}
 with torch.no_grad():
     O.pretrain_forward(params, O.make_teacher(params), ocfg, x, ids, 2, taps=otaps)
 for prec in ("bf16", "fp32"):
-    for center in ((True, False) if prec == "bf16" else (False,)):
+    for center in (False,):
         eng = PretrainEngine(Cfg.no_randomness(Cfg.shipped_large()), "cuda", precision=prec, init=params)
-        eng.center_targets = center
         taps = {}
         eng.forward(x.cuda(), ids, 2, taps=taps, need_grad=False)
         print(prec, "center", center, "targets rel", rel(taps["targets"], otaps["targets"]),
