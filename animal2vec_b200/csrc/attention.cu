@@ -16,6 +16,7 @@
 //                             in shared memory, all five products on tcgen05 with TMEM accumulators.
 //   attn_qk_bound_kernel    : max |q|, max |k| per head (the data-dependent part of the ALiBi key-tile window).
 //   attn_*_ref_kernel       : fp32 CUDA-core kernels for the fp32 validation mode.
+#include <stdlib.h>
 #include "attention_common.cuh"
 
 namespace a2v {
@@ -37,26 +38,6 @@ constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximu
 // fp32 softmax, nn/modalities/modules.py:396-399, rounds such terms away as well).
 constexpr float ATT_SKIP_LOG2 = 50.0f;
 
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Flash-style forward. One thread per query row; per 128-key tile:
 //   S = Q K^T (tcgen05, TMEM)  ->  ONE TMEM read into registers, ALiBi + running max in log2 units
@@ -582,7 +563,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             if ((int)blockIdx.x < heads_total) load_head(blockIdx.x);
             for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
                 BT_TR(0);
-                mbar_wait(bar_load, it & 1);
+                mbar_wait_sleep(bar_load, it & 1);
                 tc_fence_after();
                 BT_TR(2);
                 issue_s(0);
@@ -591,7 +572,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                     const uint64_t qd = BT_ADV(dQ_base, m * 16384), gd = BT_ADV(dG_base, m * 16384);
                     const int krows = m == 0 ? 8 : 2;  // 16-row K steps over the query rows of this tile
                     // P written -> dP_m = dO_m V^T (the TMEM columns of S), dV += Pd_m^T dO_m
-                    mbar_wait(bar_p, ph_tile);
+                    mbar_wait_sleep(bar_p, ph_tile);
                     tc_fence_after();
                     BT_TR(4 + 5 * m);
 #pragma unroll
@@ -599,7 +580,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                         umma_bf16(tmem_base + BT_TM_S, BT_ADV(gd, k * 32), BT_ADV(dV_kmaj, k * 32), id_s, k > 0 ? 1u : 0u);
                     umma_commit(bar_dp);
                     if (m == 0 && it > 0) {  // the previous head's dK / dV accumulators must have been read out
-                        mbar_wait(bar_epi, (it - 1) & 1);
+                        mbar_wait_sleep(bar_epi, (it - 1) & 1);
                         tc_fence_after();
                     }
                     for (int kt = 0; kt < n_kt; ++kt) {
@@ -611,7 +592,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                     }
                     BT_TR(5 + 5 * m);
                     // dS written -> S_{m+1}, dQ_m = dS_m K, dK += dS_m^T Q_m
-                    mbar_wait(bar_ds, ph_tile);
+                    mbar_wait_sleep(bar_ds, ph_tile);
                     tc_fence_after();
                     BT_TR(6 + 5 * m);
                     if (m + 1 < n_mt) issue_s(m + 1);
@@ -632,7 +613,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                     umma_commit(bar_free);
                     BT_TR(7 + 5 * m);
                     if (m == n_mt - 1) {  // operands free once every product of this head has retired
-                        mbar_wait(bar_free, ph_tile);
+                        mbar_wait_sleep(bar_free, ph_tile);
                         if (head + (int)gridDim.x < heads_total) load_head(head + gridDim.x);
                         BT_TR(13);
                     }
@@ -680,7 +661,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             const float lse_m[2] = {nx_lse0, nx_lse1};
             prefetch_head(head + gridDim.x);
             // delta_i = dO_i . O_i of both row tiles from the TMA-staged tiles (each thread: its 16 of the 64 dims)
-            mbar_wait(bar_load, it & 1);
+            mbar_wait_sleep(bar_load, it & 1);
             float delta_m[2] = {0.f, 0.f};
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -724,11 +705,11 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
 
                 // ---- P (undropped, parked in the dS buffer) and Pd (dropout applied) from S
                 if (tid == 0) BT_TR(18 + 8 * m);
-                mbar_wait(bar_s, ph_s);
+                mbar_wait_sleep(bar_s, ph_s);
                 ph_s ^= 1;
                 tc_fence_after();
                 if (tid == 0) BT_TR(19 + 8 * m);
-                if (tiles_done > 0) mbar_wait(bar_free, (tiles_done - 1) & 1);  // P / dS buffers of the previous tile
+                if (tiles_done > 0) mbar_wait_sleep(bar_free, (tiles_done - 1) & 1);  // P / dS buffers of the previous tile
                 if (row_used) {
                     const uint32_t row_key = DROP ? attn_row_key(p.seed, bh, L, i) : 0u;
                     // rows beyond L: lse = +inf makes every probability exactly 0 without a per-element test
@@ -786,7 +767,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                 if (tid == 0) BT_TR(20 + 8 * m);
 
                 // ---- dS = P * (dP * keep - delta), d(alibi scale)
-                mbar_wait(bar_dp, ph_dp);
+                mbar_wait_sleep(bar_dp, ph_dp);
                 ph_dp ^= 1;
                 tc_fence_after();
                 if (tid == 0) BT_TR(21 + 8 * m);
@@ -832,7 +813,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                 if (tid == 0) BT_TR(22 + 8 * m);
 
                 // ---- dQ rows of this tile
-                mbar_wait(bar_dq, ph_dq);
+                mbar_wait_sleep(bar_dq, ph_dq);
                 ph_dq ^= 1;
                 tc_fence_after();
                 if (tid == 0) BT_TR(23 + 8 * m);
@@ -858,7 +839,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                 ++tiles_done;
             }
             // ---- dK, dV rows: quarter -> (dK | dV, key tile); final once the last tile's products retired
-            mbar_wait(bar_free, (tiles_done - 1) & 1);
+            mbar_wait_sleep(bar_free, (tiles_done - 1) & 1);
             tc_fence_after();
             if (tid == 0) BT_TR(39);
             {
@@ -1096,15 +1077,17 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         attn_fwd_ref_kernel<<<grid, 128, 0, st>>>(p);
         return a2v_check_launch("attn_fwd_ref");
     }
-    static EncodeTiledFn2 encode = nullptr;
+    // short sequences (the student's kept tokens): persistent single-pass kernel; A2V_ATTN_SHORT=0 keeps the flash kernel
+    static int use_short = -1;
+    if (use_short < 0) {
+        const char* e = getenv("A2V_ATTN_SHORT");
+        use_short = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (use_short == 1 && p.L <= ATTN_SHORT_LMAX) return attn_fwd_short_launch(p, st);
+    EncodeTiledFn2 encode = attn_tensor_map_encoder();
     if (encode == nullptr) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym) {
-            a2v_set_error("attention: cuTensorMapEncodeTiled not available");
-            return A2V_ERR_CUDA;
-        }
-        encode = reinterpret_cast<EncodeTiledFn2>(sym);
+        a2v_set_error("attention: cuTensorMapEncodeTiled not available");
+        return A2V_ERR_CUDA;
     }
     A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0, "attention: qkv not 16-byte aligned");
     CUtensorMap tm;
