@@ -52,7 +52,8 @@ def _launch(d: L.GemmDesc, anchor: torch.Tensor) -> None:
     e0.record()
     L.check(L.load().a2v_gemm(C.byref(d), L.stream_ptr()), "a2v_gemm")
     e1.record()
-    tl.append((e0, e1, _flops(d)))
+    kind = "linear" if (d.taps == 1 and d.groups == 1 and d.batch == 1) else "tap"
+    tl.append((e0, e1, _flops(d), kind))
 
 
 def _rows2d(t: torch.Tensor) -> tuple[int, int, int]:
@@ -213,7 +214,7 @@ def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: 
     L.check(L.load().a2v_conv_slab_fwd(C.byref(d), L.stream_ptr()), "a2v_conv_slab_fwd")
     if tl is not None:
         e1.record()
-        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps))
+        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps, "slab"))
     return out
 
 
@@ -243,7 +244,7 @@ def conv_slab_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, tap
         e0.record()
         fn()
         e1.record()
-        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps))
+        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps, "slab"))
     else:
         fn()
     return out

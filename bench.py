@@ -29,6 +29,21 @@ METRIC = "pretrain 10s-clip samples/sec"
 WORKLOAD = ("animal2vec-{model} pretraining step (configs[2]), 10-s 8 kHz clips, M=12 clones, EMA teacher, mixup, dropout, "
             "AdamW + clip + EMA update in the step")
 UNIT = "samples/s"
+# the other BASELINE.json configs, measured on request (--workload); the driver's default run is the headline above
+ALT = {
+    "fe": {"metric": "feature extractor fwd+bwd 10s-clip samples/sec",
+           "workload": "SincNet + conv feature extractor + project_features forward/backward alone (configs[1]), bf16, "
+                       "10-s 8 kHz clips", "flop_per_clip": 3 * 53.5e9, "batch": 64},
+    "48k": {"metric": "pretrain 10s-clip samples/sec (48 kHz)",
+            "workload": "animal2vec-large pretraining step on 10-s 48 kHz clips (configs[4]): 480 000 samples, T = 12 000 "
+                        "frames, ~790 kept tokens per clone, M=12 clones, EMA teacher, mixup, dropout, AdamW + clip + EMA",
+            "flop_per_clip": 50.6e12, "batch": 3},
+    "finetune": {"metric": "finetune 10s-clip samples/sec",
+                 "workload": "animal2vec-large finetuning step (configs[3]): 12-class frame-level multilabel head on the "
+                             "mean of the top-16 FFN outputs, focal loss, time + channel masking, layerdrop, source + target "
+                             "mixup, full-length (T = 2000) student with gradients, frozen conv extractor, AdamW",
+                 "flop_per_clip": 4.93e12, "flop_per_clip_frozen": 1.68e12, "batch": 24},
+}
 
 
 def parse_args():
@@ -37,12 +52,27 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("A2V_BENCH_BATCH", "24")),
-                    help="clips per GPU per step (the reference's yaml uses 5 on unnamed GPUs)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("A2V_BENCH_BATCH", "0")),
+                    help="clips per GPU per step (default: 24 for the headline; the reference's yaml uses 5 on unnamed GPUs)")
     ap.add_argument("--model", default="large", choices=["large", "tiny"])
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "fe", "48k", "finetune"],
+                    help="pretrain = the headline (BASELINE configs[2]); fe / 48k / finetune = configs[1] / [4] / [3]")
+    ap.add_argument("--frozen", action="store_true", help="finetune workload: the frozen phase (only the head trains)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0)
     return ap.parse_args()
+
+
+def traffic_per_launch(kernel: str):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the named kernel from the committed ncu
+    --set full capture of this bench command (profiles/r2_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -145,8 +175,10 @@ def time_cpu_port(model: str, steps: int, warmup: int, budget_s: float):
         if time.perf_counter() - t_start > budget_s and len(times) >= 1:
             break
     per = sum(times) / len(times)
-    note = (f"{len(times)} timed step(s) of 1 clip x {cfg.clone_batch} clones, {model} config, fp32, forward+backward+EMA, "
-            f"oracle/a2v_oracle.py on torch CPU ({cores} threads), mixup off")
+    note = (f"{len(times)} timed step(s) after {warmup} warm-up of 1 clip x {cfg.clone_batch} clones, {model} config, fp32, "
+            f"forward+backward+EMA, oracle/a2v_oracle.py (port) on torch CPU ({cores} threads), mixup off. Deviates from "
+            f"BASELINE.md section 4 (base config, B=2, the shimmed reference itself): the GPU box has no /root/reference and "
+            f"the headline config is large; mean of the timed steps, not best-of-3")
     return 1.0 / per, cores, len(times), per, note
 
 
@@ -196,7 +228,7 @@ def run_b200(args):
 
     cfg = Cfg.shipped_large() if args.model == "large" else Cfg.tiny()
     n = 80000 if args.model == "large" else 16000
-    B = args.batch
+    B = args.batch or 24
     eng = PretrainEngine(cfg, dev, precision="bf16", init_seed=0, rng_seed=1 + rank)
     trainer = PretrainTrainer(eng, OptimConfig())
 
@@ -275,8 +307,11 @@ def run_b200(args):
     ms_total, clocks = timed(step_resident, args.steps, sampler)
     launches = L.launch_count - launches0
     tl, L.gemm_timeline = L.gemm_timeline, None
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in tl)
-    gemm_flops = sum(f for _, _, f in tl)
+    fam = {}
+    for a, b, f, kind in tl:
+        e = fam.setdefault(kind, [0.0, 0.0, 0])
+        e[0] += a.elapsed_time(b); e[1] += f; e[2] += 1
+    gemm_ms, gemm_flops, gemm_n = fam.get("linear", [0.0, 0.0, 0])
     log = trainer.log_values()
     # ---- end-to-end leg (host buffers, H2D + D2H inside the timed region)
     step_e2e(0)
@@ -300,11 +335,22 @@ def run_b200(args):
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * n * 4, "d2h_bytes_per_step": 16,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 GEMM kernels: gemm2cta (CTA pairs, block Linears) + gemm_tcgen05 (all other GEMM / strided-conv launches)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "gemm2cta_kernel / gemm2cta_tn_kernel (CTA-pair tcgen05 GEMM) + gemm_tcgen05_kernel on the plain "
+                               "Linear shapes (QKV, proj, fc1, fc2, decoder / feature projections, strided-conv GEMMs; forward, "
+                               "data and weight gradients): every launch with taps = groups = batch = 1",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic_per_launch("gemm2cta"),
+                     "flops": "algorithmic = executed for these shapes (2 M N K, no padding)",
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                     "launches": len(tl), "share_of_step": gemm_ms / ms_total},
+                     "launches": gemm_n, "share_of_step": gemm_ms / ms_total,
+                     "other_tensor_kernels": {
+                         k: {"ms_per_step": v[0] / args.steps, "tflops_executed": v[1] / (v[0] / 1e3) / 1e12 if v[0] else None,
+                             "launches": v[2], "share_of_step": v[0] / ms_total,
+                             "note": ("conv_slab_fwd / conv_slab_wgrad (grouped stride-1 convs); executed FLOPs count the decoder's "
+                                      "48-wide groups as 64 (x1.33 of algorithmic there), exact for the positional convs")
+                             if k == "slab" else "gemm_tcgen05_kernel tap-loop / grouped launches"}
+                         for k, v in fam.items() if k != "linear"}},
         "step_tensor_frac": (flop_clip * value / world / 1e12 / peaks["tflops_sustained"]) if flop_clip else None,
         "loss": log.get("loss"), "gnorm": log.get("gnorm"), "pred_var": log.get("pred_var"),
         "target_var": log.get("target_var"),
@@ -313,7 +359,7 @@ def run_b200(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                val, cores, done, per, note = time_cpu_port(args.model, 1, 0, 60.0)
+                val, cores, done, per, note = time_cpu_port(args.model, 3, 1, 90.0)
                 line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": note}
             except Exception as ex:  # the baseline is a reported number, never the product
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -323,10 +369,223 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (--workload fe | 48k | finetune), one GPU or data parallel
+# --------------------------------------------------------------------------------------------------
+def run_alt(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200 import lib as L
+    from animal2vec_b200 import ops
+    from animal2vec_b200.engine import PretrainEngine
+    from animal2vec_b200.trainer import OptimConfig, PretrainTrainer, cosine_lr
+
+    spec = ALT[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the kernels are sm_100a-only and there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    B = args.batch or spec["batch"]
+    tiny = args.model == "tiny"
+    sr = 48000 if args.workload == "48k" else 8000
+    n = (96000 if tiny else 480000) if args.workload == "48k" else (16000 if tiny else 80000)
+    pool = 3
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = [F.layer_norm(torch.randn(B, n, generator=g), (n,)).pin_memory() for _ in range(pool)]
+    devb = [h.to(dev) for h in host]
+    staging = torch.empty(B, n, device=dev)
+    out_host = torch.empty(2, dtype=torch.float64).pin_memory()
+    extra = {}
+
+    if args.workload == "fe":
+        cfg = Cfg.tiny() if tiny else Cfg.shipped_large()
+        eng = PretrainEngine(cfg, dev, precision="bf16", init_seed=0)
+        eng._refresh_student()
+        T = eng.frames_for(n)
+        dlf = (torch.randn(B * T, eng.D, device=dev) * 1e-2).bfloat16()
+        acc = torch.zeros(2, device=dev, dtype=torch.float64)
+
+        def step(x):
+            from types import SimpleNamespace
+            c = SimpleNamespace()
+            eng.zero_grad()
+            lf = eng._fe_forward(x, c, True)
+            eng._fe_backward(c, dlf)
+            eng._unpack_grads()
+            return lf
+
+        def result_of(lf):
+            ops.sumsq(eng.S.grad, acc[0:1].zero_())
+            return acc
+        h2d, d2h = B * n * 4, 16
+        extra["hbm_algorithmic_gbs_note"] = "fused lower bound 2.4 MB/clip forward (SURVEY 8d); this chain is unfused"
+    elif args.workload == "48k":
+        cfg = Cfg.tiny(sample_rate=sr) if tiny else Cfg.shipped_large(sample_rate=sr)
+        eng = PretrainEngine(cfg, dev, precision="bf16", init_seed=0, rng_seed=1 + rank)
+        trainer = PretrainTrainer(eng, OptimConfig())
+        k = [0]
+
+        def step(x):
+            i = k[0]; k[0] += 1
+            return trainer.train_step([(x, [(i * world + rank) * B + j for j in range(B)])])
+
+        def result_of(out):
+            return out["stats"][0:2]
+        h2d, d2h = B * n * 4, 16
+    else:
+        from animal2vec_b200.finetune import FinetuneEngine
+        mcfg = Cfg.tiny() if tiny else Cfg.shipped_large()
+        ft = Cfg.shipped_finetune(freeze_finetune_updates=(10 ** 9 if args.frozen else 0))
+        if tiny:
+            ft.average_top_k_layers, ft.mask_channel_length = 2, 16
+        fe = FinetuneEngine(mcfg, ft, 12, dev, precision="bf16", init_seed=0, rng_seed=1 + rank, metric_threshold=0.175)
+        eng = fe.core
+        T = eng.frames_for(n)
+        tg = torch.Generator().manual_seed(99 + rank)
+        tgt_host = [(torch.rand(B, T, 12, generator=tg) < 0.05).float().pin_memory() for _ in range(pool)]
+        tgt_dev = [t.to(dev) for t in tgt_host]
+        tgt_stage = torch.empty(B, T, 12, device=dev)
+        oc = OptimConfig(lr=3e-5, warmup_updates=2000, warmup_init_lr=1e-10, min_lr=5e-6, max_update=30000, eps=1e-8,
+                         weight_decay=0.0, clip_norm=0.0)  # finetune_mixup_100.yaml:62-79
+        m1, v1 = torch.zeros_like(eng.S.data), torch.zeros_like(eng.S.data)
+        m2, v2 = torch.zeros_like(fe.head), torch.zeros_like(fe.head)
+        coef = torch.zeros(2, device=dev, dtype=torch.float32)
+        denom = torch.zeros(1, device=dev, dtype=torch.float32)
+        sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
+        k = [0]
+        tcur = [None]
+
+        def step(x):
+            i = k[0]; k[0] += 1
+            fe.zero_grad()
+            res = fe.forward(x, tcur[0], training=True)
+            fe.backward()
+            if world > 1:  # legacy_ddp-style flat all-reduce (finetune yaml), head + encoder
+                dist.all_reduce(fe.head_grad)
+                if fe.encoder_trainable:
+                    dist.all_reduce(eng.S.grad)
+            # fairseq: grads * 1 / sample_size (ntokens), adam (no clip in the finetune recipe)
+            denom.fill_(float(res["sample_size"] * world))
+            sumsq.zero_()
+            ops.clip_coef(sumsq, denom, 1.0, 0.0, coef)
+            lr = cosine_lr(oc, fe.num_updates)
+            fe.num_updates += 1
+            kw = dict(lr=lr, beta1=0.9, beta2=0.98, eps=oc.eps, weight_decay=0.0, step=fe.num_updates, grad_scale=coef[0:1])
+            if fe.encoder_trainable or not args.frozen:
+                ops.adamw_step(eng.S.data, eng.S.grad, m1, v1, eng.S16, **kw)
+                eng.mark_student_updated(s16_valid=True)
+            ops.adamw_step(fe.head, fe.head_grad, m2, v2, None, **kw)
+            return res
+
+        def result_of(res):
+            return res["loss_sum"]
+        h2d, d2h = B * n * 4 + B * T * 12 * 4, 8
+        spec = dict(spec)
+        if args.frozen:
+            spec["flop_per_clip"] = spec["flop_per_clip_frozen"]
+            spec["workload"] += " -- FROZEN phase (freeze_finetune_updates not reached: encoder forward only, head trains)"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.mark_begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s_ in range(steps):
+            fn(s_)
+        e1.record()
+        barrier()
+        if sampler:
+            sampler.mark_end()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    cnt = [0]
+
+    def resident(s_):
+        i = cnt[0]; cnt[0] += 1
+        if args.workload == "finetune":
+            tcur[0] = tgt_dev[i % pool]
+        step(devb[i % pool])
+
+    def e2e(s_):
+        i = cnt[0]; cnt[0] += 1
+        staging.copy_(host[i % pool], non_blocking=True)
+        if args.workload == "finetune":
+            tgt_stage.copy_(tgt_host[i % pool], non_blocking=True)
+            tcur[0] = tgt_stage
+        out = step(staging)
+        r = result_of(out)
+        out_host[: r.numel()].copy_(r.view(-1)[:2].double(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for s_ in range(args.warmup):
+        resident(s_)
+    L.gemm_timeline = []
+    launches0 = L.launch_count
+    ms_total, clocks = timed(resident, args.steps, sampler)
+    launches = L.launch_count - launches0
+    tl, L.gemm_timeline = L.gemm_timeline, None
+    t_ms = sum(a.elapsed_time(b) for a, b, _, _ in tl)
+    t_fl = sum(f for _, _, f, _ in tl)
+    e2e(0)
+    ms_e2e, _ = timed(e2e, args.steps)
+    peaks = measured_peaks()
+    clips = world * B * args.steps
+    value = clips / (ms_total / 1e3)
+    line = {
+        "metric": spec["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": spec["workload"] + (" [tiny model: smoke run]" if tiny else ""), "clips_per_gpu_per_step": B,
+                   "global_batch": B * world, "samples_per_clip": n, "parallelism": f"dp{world}",
+                   "l2_policy": "a different synthetic batch every step; activations exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": clips / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "all tcgen05 GEMM / slab-conv launches of the step (executed FLOPs)",
+                     "achieved": t_fl / (t_ms / 1e3) / 1e12 if t_ms else None, "peak": peaks["tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": (t_fl / (t_ms / 1e3) / 1e12 / peaks["tflops_sustained"]) if t_ms else None,
+                     "traffic": None, "share_of_step": t_ms / ms_total if ms_total else None,
+                     "peak_source": peaks["source"] + ", sustained figure"},
+        "step_tensor_frac": spec["flop_per_clip"] * value / world / 1e12 / peaks["tflops_sustained"] if not tiny else None,
+        "mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+    }
+    line.update(extra)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "pretrain":
+        run_alt(args)
     else:
         run_b200(args)
 
