@@ -536,7 +536,7 @@ static int g2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Pa
 }
 
 static int g2_try_tn(const a2v_gemm_desc* d, cudaStream_t st) {
-    if (d->taps != 1 || d->batch != 1 || d->groups != 1 || d->a_tap_cols != 0 || d->c_dtype != A2V_F32) return -1;
+    if (d->taps != 1 || d->batch != 1 || d->groups != 1 || d->a_tap_cols != 0 || d->a_tap_wrap != 0 || d->c_dtype != A2V_F32) return -1;
     if (!d->out_atomic || d->M % 256 != 0 || d->N % 256 != 0 || d->ldc % 4 != 0 || d->red_rows < 64 * 16) return -1;
     if (d->a_row_off != 0 || d->b_row_off != 0 || d->c_row_off != 0) return -1;
     if (d->a.dim2 != 1 || d->b.dim2 != 1 || d->a.stride1 % 8 != 0 || d->b.stride1 % 8 != 0) return -1;

@@ -28,6 +28,7 @@ struct GemmParams {
     int kb_per_tap, taps, batch, groups;
     int m_tiles, n_tiles;
     int a_group_stride, a_row_off, a_tap_rows, a_tap_cols;
+    int a_tap_wrap, a_grow_add, a_grow_div;  // strided-conv addressing (see a2v_gemm_desc)
     int b_group_stride, b_row_off, b_tap_rows;
     int red_rows, kb_per_batch, k_splits;
     void* c;
@@ -284,8 +285,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (MODE == 0) {
                         const int tap = kb / p.kb_per_tap;
                         const int kc = kb - tap * p.kb_per_tap;
-                        tma_load_3d(sa, &tmA, &full_bar[stage], t.g * p.a_group_stride + kc * BLOCK_K,
-                                    t.m_tile * BLOCK_M + tap * p.a_tap_rows + p.a_row_off, t.b);
+                        int arow = t.m_tile * BLOCK_M + tap * p.a_tap_rows + p.a_row_off;
+                        int acol = t.g * p.a_group_stride + kc * BLOCK_K;
+                        if (p.a_tap_wrap > 0) {  // strided conv: (B, T, C) viewed as (B, T/s, s*C)
+                            const int q = tap + p.a_row_off;
+                            const int rq = q >= 0 ? q / p.a_tap_wrap : -((-q + p.a_tap_wrap - 1) / p.a_tap_wrap);
+                            arow = t.m_tile * BLOCK_M + rq;
+                            acol += (q - rq * p.a_tap_wrap) * p.a_tap_cols;
+                        }
+                        if (p.a_grow_div > 0) arow += (t.g + p.a_grow_add) / p.a_grow_div;
+                        tma_load_3d(sa, &tmA, &full_bar[stage], acol, arow, t.b);
                         tma_load_3d(sb, &tmB, &full_bar[stage], kb * BLOCK_K,
                                     t.g * p.b_group_stride + t.n_tile * BLOCK_N, 0);
                     } else {
@@ -298,9 +307,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const int m0 = t.m_tile * BLOCK_M + i * 64;
                             const int tap = p.a_tap_cols > 0 ? m0 / p.a_tap_cols : 0;
                             const int c0 = m0 - tap * p.a_tap_cols;
-                            tma_load_3d(sa + i * (64 * BLOCK_K * 2), &tmA, &full_bar[stage],
-                                        t.g * p.a_group_stride + c0,
-                                        r0 + (p.a_tap_cols > 0 ? tap * p.a_tap_rows + p.a_row_off : 0), b);
+                            int arow = r0 + (p.a_tap_cols > 0 ? tap * p.a_tap_rows + p.a_row_off : 0);
+                            int acol = t.g * p.a_group_stride + c0;
+                            if (p.a_tap_wrap > 0) {  // strided conv weight gradient: x viewed as (B, T/s, s*C)
+                                const int q = tap + p.a_row_off;
+                                const int rq = q >= 0 ? q / p.a_tap_wrap : -((-q + p.a_tap_wrap - 1) / p.a_tap_wrap);
+                                arow = r0 + rq;
+                                acol += (q - rq * p.a_tap_wrap) * p.a_tap_cols;
+                            }
+                            tma_load_3d(sa + i * (64 * BLOCK_K * 2), &tmA, &full_bar[stage], acol, arow, b);
                         }
 #pragma unroll
                         for (int i = 0; i < BLOCK_N / 64; ++i)
@@ -699,6 +714,7 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
     A2V_REQUIRE(d->block_n == 64 || d->block_n == 128 || d->block_n == 256, "gemm: block_n must be 64, 128 or 256");
     A2V_REQUIRE(d->M > 0 && d->N > 0, "gemm: empty output (M=%d N=%d)", d->M, d->N);
     A2V_REQUIRE(d->taps >= 1 && d->batch >= 1 && d->groups >= 1, "gemm: taps/batch/groups must be >= 1");
+    A2V_REQUIRE(d->a_tap_wrap >= 0 && d->a_grow_div >= 0, "gemm: a_tap_wrap / a_grow_div must be >= 0");
     A2V_REQUIRE(d->c != nullptr, "gemm: C is NULL");
     A2V_REQUIRE(d->c_dtype == A2V_F32 || d->c_dtype == A2V_BF16, "gemm: bad c_dtype");
     A2V_REQUIRE(!(d->out_atomic || d->out_accumulate) || d->c_dtype == A2V_F32,
@@ -730,6 +746,9 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
     p.a_row_off = d->a_row_off;
     p.a_tap_rows = d->a_tap_rows;
     p.a_tap_cols = d->a_tap_cols;
+    p.a_tap_wrap = d->a_tap_wrap;
+    p.a_grow_add = d->a_grow_add;
+    p.a_grow_div = d->a_grow_div;
     p.b_group_stride = d->b_group_stride;
     p.b_row_off = d->b_row_off;
     p.b_tap_rows = d->b_tap_rows;
@@ -760,13 +779,17 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         p.num_tiles = p.n_tiles * p.m_tiles * p.batch * p.groups;
         if ((rc = make_map(&ta, d->a, BLOCK_M, "A")) != A2V_OK) return rc;
         if ((rc = make_map(&tb, d->b, d->block_n, "B")) != A2V_OK) return rc;
-        A2V_REQUIRE(d->a_tap_cols == 0, "gemm: a_tap_cols is a TN-mode field");
+        A2V_REQUIRE(d->a_tap_cols == 0 || d->a_tap_wrap > 0, "gemm: NT mode takes a_tap_cols only with a_tap_wrap (strided conv)");
+        A2V_REQUIRE(d->a_tap_wrap == 0 || (d->a_tap_cols > 0 && d->a_tap_cols % 8 == 0 && d->a_tap_cols == d->k_per_tap),
+                    "gemm: strided conv needs a_tap_cols == k_per_tap (channels per input row)");
     } else {
         A2V_REQUIRE(d->red_rows > 0 && d->k_splits >= 1, "gemm: TN mode needs red_rows > 0 and k_splits >= 1");
         A2V_REQUIRE(d->k_splits == 1 || d->out_atomic, "gemm: split-K requires out_atomic");
         A2V_REQUIRE(d->bias == nullptr, "gemm: TN mode has no bias epilogue");
         A2V_REQUIRE(d->a_tap_cols == 0 || (d->a_tap_cols > 0 && d->a_tap_cols % 64 == 0 && d->taps == 1),
                     "gemm: a_tap_cols must be a multiple of 64 (and taps == 1: the taps live in M)");
+        A2V_REQUIRE(d->a_tap_wrap == 0 || d->a_tap_cols > 0, "gemm: a_tap_wrap needs a_tap_cols");
+        A2V_REQUIRE(d->a_grow_div == 0, "gemm: a_grow_div is an NT-mode field");
         p.red_rows = d->red_rows;
         p.kb_per_batch = ceil_div(d->red_rows, BLOCK_K);
         p.k_splits = d->k_splits;

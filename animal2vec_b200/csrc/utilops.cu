@@ -392,6 +392,17 @@ __global__ void clip_coef_kernel(const double* __restrict__ sumsq, const float* 
     out[1] = norm;
 }
 
+// out[8 i .. 8 i + 7] = float(in[...]): the bf16 gradient buckets coming back from the all-reduce
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out,
+                                                            long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = *reinterpret_cast<const uint4*>(in + 8 * i);
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        *reinterpret_cast<float4*>(out + 8 * i) = make_float4(a.x, a.y, b.x, b.y);
+        *reinterpret_cast<float4*>(out + 8 * i + 4) = make_float4(c.x, c.y, d.x, d.y);
+    }
+}
+
 static int flat_grid(long long n) {
     long long b = ceil_div64(n, 256);
     long long cap = (long long)a2v_num_sms() * 8;
@@ -550,6 +561,14 @@ extern "C" int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_s
     if (n == 0) return A2V_OK;
     cast_f32_bf16_kernel<<<flat_grid(n / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, (bf16*)out, n / 4);
     return a2v_check_launch("cast_f32_to_bf16");
+}
+
+extern "C" int a2v_cast_bf16_to_f32(const void* in, float* out, int64_t n, a2v_stream_t stream) {
+    A2V_REQUIRE(in && out && n >= 0 && n % 8 == 0, "cast_bf16_to_f32: n must be a multiple of 8");
+    A2V_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, "cast_bf16_to_f32: 16-byte alignment");
+    if (n == 0) return A2V_OK;
+    cast_bf16_f32_kernel<<<flat_grid(n / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)in, out, n / 8);
+    return a2v_check_launch("cast_bf16_to_f32");
 }
 
 extern "C" int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream) {

@@ -71,6 +71,7 @@ class _Weights:
         self.dgrad: Dict[str, torch.Tensor] = {}  # name -> bf16 operand of the data-gradient product
         self.split: Dict[str, int] = {}           # name -> K granularity of the fp32-mode split (fwd)
         self.split_d: Dict[str, int] = {}
+        self.dgrad_s: Dict[str, torch.Tensor] = {}  # name -> operand of the im2col-free strided data gradient
         self.f32: Dict[str, torch.Tensor] = {}    # name -> fp32 view / padded fp32 buffer (biases, norms)
         self.alibi: Optional[torch.Tensor] = None
 
@@ -246,7 +247,9 @@ class PretrainEngine:
             n = le + f"{i}.0.weight"
             sp[n + "|F"] = P.pack_conv_fwd(n, 1, c, cin, k, cgp=cinp)
             if st > 1:
-                sp[n + "|T"] = P.pack_col_t(n, c, cin, k, cinp)
+                sp[n + "|T"] = P.pack_col_t(n, c, cin, k, cinp)  # im2col fallback (fp32 mode, odd clip lengths)
+                if not self.fp32:  # im2col-free strided path (gemm.strided_conv_*)
+                    sp[n + "|S"] = P.pack_conv_dgrad_strided(n, c, cin, k, st, int(math.ceil(st / 2)), cinp)
             else:
                 sp[n + "|T"] = P.pack_conv_dgrad(n, 1, c, cin, k, cgp=cinp)
             cin, cinp = c, c
@@ -283,7 +286,7 @@ class PretrainEngine:
         self.gpacked: Dict[str, torch.Tensor] = {}
         self.gt_keys = set()
         for i, (_c, _k, st) in enumerate(self.layers[1:], start=1):
-            if st == 1:
+            if st == 1 or not self.fp32:  # bf16: the strided layers' weight gradients use the transposed layout too
                 self.gt_keys.add(le + f"{i}.0.weight|F")
         for n in self.pos_names:
             self.gt_keys.add(n + "|F")
@@ -318,11 +321,14 @@ class PretrainEngine:
             name, kind = key.split("|")
             buf = P.materialize(pk, S.view(name), self.fp32)
             if table is not None:
-                table.add(S.view(name), buf, pk.dims, pk.in_strides, pk.in_off, pk.out_strides, 0)
+                for dims, ist, ioff, ost, ooff in pk.parts:
+                    table.add(S.view(name), buf, dims, ist, ioff, ost, ooff)
             if kind == "F":
                 W.fwd[name], W.split[name] = buf, pk.split_k
             elif kind == "T":
                 W.dgrad[name], W.split_d[name] = buf, pk.split_k
+            elif kind == "S":
+                W.dgrad_s[name] = buf
             else:
                 W.f32[name] = buf
         for n in S.names:
@@ -442,10 +448,15 @@ class PretrainEngine:
             if st > 1:
                 pad = int(math.ceil(st / 2))  # nn/utils.py:1089
                 tout = (tin + 2 * pad - k) // st + 1
-                col = ops.im2col(xin, k, st, pad, tout)
-                y = self.lin(col, W, n)
-                if not (save and self.keep_im2col):
+                if not self.fp32 and gemm.strided_conv_ok(tin, cinp, k, st, pad):
+                    # input viewed as (B, T/st, st*C): no im2col buffer (85 MB per clip in the large config)
                     col = None
+                    y = gemm.strided_conv_nt(xin, W.fwd[n], taps=k, stride=st, pad=pad, out_dtype=self.adt)
+                else:
+                    col = ops.im2col(xin, k, st, pad, tout)
+                    y = self.lin(col, W, n)
+                    if not (save and self.keep_im2col):
+                        col = None
             else:
                 col = None
                 y = self.conv(xin, W, n, taps=k, pad=(k - 1) // 2, groups=1)  # padding="same"
@@ -836,13 +847,21 @@ class PretrainEngine:
             if st > 1:
                 pad = int(math.ceil(st / 2))
                 tout = dy.shape[1]
-                col = s.col if s.col is not None else ops.im2col(xin, k, st, pad, tout)
-                self.wgrad(dy, col, self.gpacked[n + "|F"])
-                del col
-                s.col = None
-                dcol = self.lin(dy, W, n, dgrad=True)
-                da = ops.col2im(dcol.view(b, tout, k * cinp), k, st, pad, tin)
-                del dcol
+                if not self.fp32 and gemm.strided_conv_ok(tin, cinp, k, st, pad):
+                    gemm.strided_conv_wgrad_tn(dy, xin, self.gpacked[n + "|F"], taps=k, stride=st, pad=pad)
+                    da = gemm.strided_conv_dgrad(dy, W.dgrad_s[n], c=cinp, taps_per_block=-(-k // st), stride=st, pad=pad,
+                                                 out_dtype=self.adt)
+                else:
+                    col = s.col if s.col is not None else ops.im2col(xin, k, st, pad, tout)
+                    if self.fp32:
+                        self.wgrad(dy, col, self.gpacked[n + "|F"])
+                    else:  # same transposed (k*C, N) layout as the strided path writes
+                        gemm.gemm_tn(col.reshape(-1, col.shape[-1]), dy.reshape(-1, dy.shape[-1]), self.gpacked[n + "|F"])
+                    del col
+                    s.col = None
+                    dcol = self.lin(dy, W, n, dgrad=True)
+                    da = ops.col2im(dcol.view(b, tout, k * cinp), k, st, pad, tin)
+                    del dcol
             else:
                 self.conv_wgrad(dy, xin, self.gpacked[n + "|F"], taps=k, pad=(k - 1) // 2, groups=1)
                 da = self.conv(dy, W, n, taps=k, pad=k - 1 - (k - 1) // 2, groups=1, dgrad=True)

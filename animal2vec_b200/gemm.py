@@ -174,6 +174,106 @@ def conv_nt(
     return out
 
 
+def strided_conv_ok(t_in: int, c: int, k: int, stride: int, pad: int) -> bool:
+    """The im2col-free strided path: T divisible by the stride, output length T / stride, 64-multiple channels."""
+    return stride > 1 and t_in % stride == 0 and (t_in + 2 * pad - k) // stride + 1 == t_in // stride and c % 64 == 0
+
+
+def strided_conv_nt(x: torch.Tensor, w: torch.Tensor, *, taps: int, stride: int, pad: int,
+                    out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Strided Conv1d (nn/utils.py:1085-1092) over channels-last activations WITHOUT im2col.
+
+    ``x``: (B, T, C) bf16, ``w``: (N, taps*C) bf16 tap-major (params.pack_conv_fwd); returns (B, T/stride, N):
+        y[b, t, n] = sum_{j, c} x[b, stride*t + j - pad, c] * w[n, j*C + c]        (zero padding).
+    x is addressed as (B, T/stride, stride*C): input row stride*t + q = (row t + floor(q/stride), column block q mod stride).
+    """
+    bsz, t, c = x.shape
+    assert x.is_contiguous() and w.is_contiguous() and strided_conv_ok(t, c, taps, stride, pad)
+    n = w.shape[0]
+    assert w.shape[1] == taps * c
+    tout = t // stride
+    out = torch.empty(bsz, tout, n, device=x.device, dtype=out_dtype or torch.bfloat16)
+    d = L.GemmDesc()
+    d.mode = 0
+    d.block_n = _pick_block_n(n)
+    d.a = _operand(x, stride * c, tout, bsz, stride * c, t * c)
+    d.b = _operand(w, taps * c, n, 1, taps * c, 0)
+    d.M, d.N, d.k_per_tap, d.taps, d.batch, d.groups = tout, n, c, taps, bsz, 1
+    d.a_group_stride, d.a_row_off, d.a_tap_rows = 0, -pad, 0
+    d.a_tap_cols, d.a_tap_wrap = c, stride
+    d.k_splits = 1
+    d.c = out.data_ptr()
+    d.c_dtype = L.dtype_code(out)
+    d.ldc = n
+    d.c_batch_stride = tout
+    d.alpha = 1.0
+    _launch(d, x)
+    return out
+
+
+def strided_conv_dgrad(dy: torch.Tensor, wd: torch.Tensor, *, c: int, taps_per_block: int, stride: int, pad: int,
+                       out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Data gradient of :func:`strided_conv_nt` without col2im. ``dy``: (B, T/stride, N); ``wd``: (stride*C,
+    taps_per_block*N) from params.pack_conv_dgrad_strided (block r = input rows congruent r mod stride, its taps
+    j = (r + pad) mod stride + stride*u, zero weights where j >= k); returns dx (B, T, C):
+        dx[b, stride*m + r, c] = sum_u sum_n dy[b, m + (r + pad)//stride - u, n] * w[n, c, (r + pad) % stride + stride*u].
+    """
+    bsz, tout, n = dy.shape
+    assert dy.is_contiguous() and wd.is_contiguous() and wd.shape == (stride * c, taps_per_block * n) and n % 64 == 0
+    dx = torch.empty(bsz, tout * stride, c, device=dy.device, dtype=out_dtype or torch.bfloat16)
+    d = L.GemmDesc()
+    d.mode = 0
+    d.block_n = _pick_block_n(c)
+    d.a = _operand(dy, n, tout, bsz, n, tout * n)
+    d.b = _operand(wd, taps_per_block * n, stride * c, 1, taps_per_block * n, 0)
+    d.M, d.N, d.k_per_tap, d.taps, d.batch, d.groups = tout, c, n, taps_per_block, bsz, stride
+    d.a_group_stride, d.a_row_off, d.a_tap_rows = 0, 0, -1
+    d.a_grow_add, d.a_grow_div = pad, stride
+    d.b_group_stride = c
+    d.k_splits = 1
+    d.c = dx.data_ptr()
+    d.c_dtype = L.dtype_code(dx)
+    d.ldc = stride * c
+    d.c_batch_stride = tout
+    d.c_group_stride = c
+    d.alpha = 1.0
+    _launch(d, dy)
+    return dx
+
+
+def strided_conv_wgrad_tn(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, taps: int, stride: int, pad: int,
+                          k_splits: Optional[int] = None) -> torch.Tensor:
+    """Weight gradient of :func:`strided_conv_nt`, atomically accumulated into fp32 ``out`` (taps*C, N) (the
+    transposed tap-major layout of conv_wgrad_tn): out[j*C + c, n] += sum_{b, t} x[b, stride*t + j - pad, c] * dy[b, t, n]."""
+    bsz, t, c = x.shape
+    tout, n = dy.shape[1], dy.shape[2]
+    assert dy.is_contiguous() and x.is_contiguous() and tout == t // stride and strided_conv_ok(t, c, taps, stride, pad)
+    assert out.dtype == torch.float32 and out.shape == (taps * c, n) and out.is_contiguous()
+    d = L.GemmDesc()
+    d.mode = 1
+    d.block_n = 64 if n <= 64 else (128 if n <= 128 else 256)
+    d.a = _operand(x, stride * c, tout, bsz, stride * c, t * c)
+    d.b = _operand(dy, n, tout, bsz, n, tout * n)
+    d.M, d.N, d.taps, d.batch, d.groups = taps * c, n, 1, bsz, 1
+    d.a_group_stride, d.a_row_off, d.a_tap_rows, d.a_tap_cols, d.a_tap_wrap = 0, -pad, 0, c, stride
+    d.b_group_stride, d.b_row_off, d.b_tap_rows = 0, 0, 0
+    d.red_rows = tout
+    tiles = -(-(taps * c) // 128) * -(-n // d.block_n)
+    kblocks = bsz * -(-tout // 64)
+    ks = k_splits or _pick_splits(tiles, kblocks)
+    per = -(-kblocks // ks)
+    d.k_splits = -(-kblocks // per)
+    d.c = out.data_ptr()
+    d.c_dtype = L.F32
+    d.out_atomic = 1
+    d.ldc = n
+    d.c_group_stride = taps * c
+    d.c_tap_stride = 0
+    d.alpha = 1.0
+    _launch(d, x)
+    return out
+
+
 def conv_slab_ok(x: torch.Tensor, w: torch.Tensor, taps: int, groups: int) -> bool:
     """The slab kernel covers bf16 tap convs with 64-channel groups and <= 64 outputs per group."""
     if x.dtype != torch.bfloat16 or x.dim() != 3 or taps > 32:

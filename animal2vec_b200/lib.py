@@ -86,6 +86,9 @@ class GemmDesc(C.Structure):
         ("residual", C.c_void_p),
         ("dgelu_u", C.c_void_p),
         ("a_tap_cols", C.c_int),
+        ("a_tap_wrap", C.c_int),
+        ("a_grow_add", C.c_int),
+        ("a_grow_div", C.c_int),
     ]
 
 

@@ -465,6 +465,12 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
+def cast_f32(src: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    assert src.dtype == torch.bfloat16 and out.dtype == torch.float32 and src.numel() == out.numel() and src.numel() % 8 == 0
+    _call("a2v_cast_bf16_to_f32", src, _p(src), _p(out), C.c_int64(src.numel()))
+    return out
+
+
 def split3(x: torch.Tensor, pattern: int) -> torch.Tensor:
     """fp32 (rows, K) -> bf16 (rows, 3K) [pattern 0/1] or (3*rows, K) [pattern 2/3]."""
     assert x.dtype == torch.float32 and x.is_contiguous()
@@ -626,3 +632,20 @@ def channel_mask_(x: torch.Tensor, chmask_u8: torch.Tensor, rows_per_clip: int) 
     assert x.is_contiguous() and chmask_u8.dtype == torch.uint8 and chmask_u8.shape[-1] == d_
     _call("a2v_channel_mask", x, L.dtype_code(x), _p(x), _p(chmask_u8), C.c_int64(x.numel() // d_), int(rows_per_clip), d_)
     return x
+
+
+# ----------------------------------------------------------------------------- input pipeline
+def clip_layer_norm(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """Per-clip F.layer_norm(feats, feats.shape) of a collated (B, N) fp32 batch."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    y = torch.empty_like(x)
+    _call("a2v_clip_layer_norm", x, _p(x), _p(y), x.shape[0], x.shape[1], C.c_float(eps))
+    return y
+
+
+def frame_labels(offsets, start, end, cat, foc, batch: int, frames: int, classes: int, wav_len: int, focal_class: int):
+    """(B, T, classes) fp32 multi-hot frame labels from flat int32 interval arrays (see a2v_frame_labels)."""
+    out = torch.empty(batch, frames, classes, device=offsets.device, dtype=torch.float32)
+    _call("a2v_frame_labels", offsets, _p(offsets), _p(start), _p(end), _p(cat), _p(foc), batch, frames, classes, wav_len,
+          focal_class, _p(out))
+    return out

@@ -148,7 +148,7 @@ class Pack:
     possibly padded buffer. ``split_k`` is the K granularity of the fp32-mode hi/lo split."""
 
     __slots__ = ("src", "dims", "in_strides", "in_off", "out_strides", "out_shape", "split_k", "buf", "fbuf", "is_bias",
-                 "gt_strides", "gt_shape")
+                 "gt_strides", "gt_shape", "extra_parts")
 
     def __init__(self, src, dims, in_strides, in_off, out_strides, out_shape, split_k, is_bias=False):
         self.src, self.dims, self.in_strides, self.in_off = src, list(dims), list(in_strides), in_off
@@ -158,6 +158,12 @@ class Pack:
         self.is_bias = is_bias
         self.gt_strides = None  # strides of the same 4-D index space in the TRANSPOSED conv weight-gradient buffer
         self.gt_shape = None
+        self.extra_parts = []   # further (dims, in_strides, in_off, out_strides, out_off) maps into the same buffer
+
+    @property
+    def parts(self):
+        """Every 4-D index map that fills this pack's buffer: (dims, in_strides, in_off, out_strides, out_off)."""
+        return [(self.dims, self.in_strides, self.in_off, self.out_strides, 0)] + list(self.extra_parts)
 
 
 def pack_linear_t(name, n_out, k_in) -> Pack:
@@ -189,6 +195,28 @@ def pack_col_t(name, c_out, cin, k, cinp) -> Pack:
     return Pack(name, (1, k, cin, c_out), (0, 1, k, cin * k), 0, (0, cinp * c_out, c_out, 1), (k * cinp, c_out), c_out)
 
 
+def pack_conv_dgrad_strided(name, c_out, cin, k, stride, pad, cinp) -> Pack:
+    """B operand of gemm.strided_conv_dgrad: torch Conv1d weight (c_out, cin, k) -> (stride*cinp, tpb*c_out) with
+    wd[r*cinp + c, u*c_out + n] = W[n, c, (r + pad) % stride + stride*u]  (zero where that tap index is >= k);
+    tpb = ceil(k / stride) taps per output column block r. One 4-D index map per block r."""
+    tpb = -(-k // stride)
+    parts = []
+    for r in range(stride):
+        j0 = (r + pad) % stride
+        nu = len(range(j0, k, stride))
+        if nu == 0:
+            continue
+        parts.append(((1, cin, nu, c_out), (0, k, stride, cin * k), j0, (0, tpb * c_out, c_out, 1), r * cinp * tpb * c_out))
+    d0 = parts[0]
+    pk = Pack(name, d0[0], d0[1], d0[2], d0[3], (stride * cinp, tpb * c_out), c_out)
+    assert d0[4] == 0 or True
+    # the first part may not start at out offset 0 (block 0 always has taps, so it does)
+    pk.extra_parts = parts[1:]
+    if d0[4] != 0:
+        raise ValueError("pack_conv_dgrad_strided: block 0 has no tap")
+    return pk
+
+
 def pack_cols_padded(name, n_out, groups, cg, cgp) -> Pack:
     """Linear weight (n_out, G*cg) whose INPUT is group padded -> (n_out, G*cgp)."""
     return Pack(name, (1, n_out, groups, cg), (0, groups * cg, cg, 1), 0, (0, groups * cgp, cgp, 1),
@@ -216,11 +244,13 @@ def materialize(p: Pack, src: torch.Tensor, fp32_mode: bool) -> torch.Tensor:
     if not fp32_mode:
         if p.buf is None:
             p.buf = torch.zeros(p.out_shape, device=dev, dtype=torch.bfloat16)
-        ops.relayout(src, p.buf, p.dims, p.in_strides, p.in_off, p.out_strides, 0)
+        for dims, ist, ioff, ost, ooff in p.parts:
+            ops.relayout(src, p.buf, dims, ist, ioff, ost, ooff)
         return p.buf
     if p.fbuf is None:
         p.fbuf = torch.zeros(p.out_shape, device=dev, dtype=torch.float32)
-    ops.relayout(src, p.fbuf, p.dims, p.in_strides, p.in_off, p.out_strides, 0)
+    for dims, ist, ioff, ost, ooff in p.parts:
+        ops.relayout(src, p.fbuf, dims, ist, ioff, ost, ooff)
     p.buf = ops.split3(p.fbuf.view(-1, p.split_k), 1).view(p.out_shape[0], 3 * p.out_shape[1])
     return p.buf
 

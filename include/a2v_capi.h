@@ -97,6 +97,17 @@ typedef struct {
     int a_tap_cols;        /* TN only, 0 = off: M index = tap * a_tap_cols + channel; the A box of tap j reads
                               rows shifted by a_row_off + j * a_tap_rows (conv weight gradient with x as the
                               M side: C[(j, c), n] = sum_t x[t + j - pad, c] * dy[t, n]) */
+    /* STRIDED Conv1d without im2col / col2im (nn/utils.py:1085-1092: Conv1d(k, stride s, padding ceil(s/2))): the
+     * channels-last input (B, T, C) is viewed as (B, T/s, s*C), so input row s*t + q is (row t + floor(q/s),
+     * column block q mod s). a_tap_wrap = s > 0 (with a_tap_cols = C) turns that on for the A operand:
+     *   NT (forward): tap j reads row m + floor((j + a_row_off)/s), columns ((j + a_row_off) mod s) * C + k, a_row_off = -pad;
+     *   TN (weight gradient, x as the M side): the A box of tap j likewise.
+     * Data gradient = grouped NT product over the s output column blocks r (dx viewed (B, T/s, s*C)); group r reads
+     * dy rows m + (r + a_grow_add) / a_grow_div - u for its tap u (a_tap_rows = -1): a_grow_div > 0 adds that per-group
+     * row shift (a_grow_add = pad, a_grow_div = s). */
+    int a_tap_wrap;
+    int a_grow_add;
+    int a_grow_div;
 } a2v_gemm_desc;
 
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);
@@ -276,6 +287,8 @@ typedef struct {
 } a2v_relayout_item;
 int a2v_relayout_batch(const a2v_relayout_item* items_device, int n_items, int blocks_per_item, a2v_stream_t stream);
 int a2v_cast_f32_to_bf16(const float* in, void* out, int64_t n, a2v_stream_t stream);
+/* inverse widening copy (n multiple of 8): the bf16 gradient buckets after the NCCL all-reduce (trainer.BucketReducer) */
+int a2v_cast_bf16_to_f32(const void* in, float* out, int64_t n, a2v_stream_t stream);
 int a2v_split3(const float* in, void* out, int64_t rows, int K, int pattern, a2v_stream_t stream);
 int a2v_ema_step(const float* student, float* shadow, void* teacher_bf16, int64_t n, float decay,
                  a2v_stream_t stream);
@@ -402,6 +415,18 @@ int a2v_focal_loss_bwd(const float* logits, const float* targets, const int32_t*
                        int rows_per_clip, float r, float alpha, float gamma, const float* grad_out, float* dlogits,
                        a2v_stream_t stream);
 int a2v_channel_mask(int dtype, void* x, const uint8_t* chmask, int64_t rows, int rows_per_clip, int D,
+                     a2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Input pipeline on the device: per-clip layer norm of a collated batch (fairseq
+ * RawAudioDataset.postprocess with task.normalize, called at nn/audio_tasks.py:332) and frame-level multi-hot targets
+ * from label intervals (nn/audio_tasks.py:336-381; intervals of clip b are [offsets[b], offsets[b+1]) in the flat
+ * start / end / cat / foc arrays, sample positions round(linspace(0, wav_len, T, endpoint=False)); focal_class = index of
+ * the "focal" class or -1).
+ * ------------------------------------------------------------------------------------ */
+int a2v_clip_layer_norm(const float* x, float* y, int B, int N, float eps, a2v_stream_t stream);
+int a2v_frame_labels(const int32_t* offsets, const int32_t* start, const int32_t* end, const int32_t* cat,
+                     const int32_t* foc, int B, int T, int C, int wav_len, int focal_class, float* out,
                      a2v_stream_t stream);
 
 #ifdef __cplusplus

@@ -180,3 +180,37 @@ def test_cta_pair_gemm_shapes_and_epilogues(m, n, k):
     out = torch.ones(n, 256, device="cuda")
     gemm.gemm_tn(a2, b2, out)
     assert _rel(out, 1 + a2.float().t() @ b2.float()) < 1e-5
+
+
+@pytest.mark.parametrize("bsz,t,c,c_real,n,k,s,pad", [(2, 4000, 128, 127, 512, 10, 5, 3), (3, 1000, 512, 512, 512, 3, 2, 1),
+                                                        (2, 640, 64, 64, 64, 3, 2, 1), (1, 80000, 128, 127, 512, 10, 5, 3)])
+def test_strided_conv_without_im2col(bsz, t, c, c_real, n, k, s, pad):
+    """Strided Conv1d forward, data gradient and weight gradient through the (B, T/s, s*C) view addressing of the tap-loop
+    GEMM (no im2col / col2im buffers) against F.conv1d autograd; c_real < c exercises the zero-padded input channel of
+    the sinc layer (127 of 128)."""
+    from animal2vec_b200 import gemm, ops
+    from animal2vec_b200 import params as P
+
+    w = _randn(n, c_real, k, scale=0.05, seed=1).float()  # fp32 master holding bf16-representable values
+    x = _randn(bsz, t, c, seed=2)
+    x[..., c_real:] = 0
+    pk_f = P.pack_conv_fwd("w", 1, n, c_real, k, cgp=c)
+    pk_d = P.pack_conv_dgrad_strided("w", n, c_real, k, s, pad, c)
+    wf = P.materialize(pk_f, w, False)
+    wd = P.materialize(pk_d, w, False)
+    xr = x.float().clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    ref = torch.nn.functional.conv1d(xr[..., :c_real].transpose(1, 2), wr, stride=s, padding=pad).transpose(1, 2)
+    assert ref.shape[1] == t // s
+    y = gemm.strided_conv_nt(x, wf, taps=k, stride=s, pad=pad)
+    assert _rel(y, ref) < 6e-3, _rel(y, ref)
+    dy = _randn(bsz, t // s, n, seed=3)
+    ref.backward(dy.float())
+    dx = gemm.strided_conv_dgrad(dy, wd, c=c, taps_per_block=-(-k // s), stride=s, pad=pad)
+    assert _rel(dx[..., :c_real], xr.grad[..., :c_real]) < 6e-3, _rel(dx[..., :c_real], xr.grad[..., :c_real])
+    assert float(dx[..., c_real:].abs().sum()) == 0.0
+    gw = torch.zeros(pk_f.gt_shape, device="cuda")
+    gemm.strided_conv_wgrad_tn(dy, x, gw, taps=k, stride=s, pad=pad)
+    got = torch.zeros_like(w)
+    P.unpack_grad(pk_f, gw, got, transposed=True)
+    assert _rel(got, wr.grad) < 6e-3, _rel(got, wr.grad)

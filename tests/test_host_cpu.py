@@ -333,3 +333,68 @@ def test_fairseq_registration_hook_against_a_stub_package(tmp_path):
     """) % (str(tmp_path), ROOT)
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "OK" in res.stdout, res.stdout + res.stderr
+
+
+# ------------------------------------------------------------------------------------------ input pipeline (8f-4)
+def _synth_clip(seed, n):
+    """Same generator as tests/golden/make_golden_labels.py."""
+    g = np.random.default_rng(seed)
+    wav = (g.standard_normal(n) * 0.1 + 0.02).astype(np.float32)
+    k = int(g.integers(3, 9))
+    start = np.sort(g.integers(0, n - 4000, k))
+    end = start + g.integers(37, 3500, k)
+    cat = g.integers(0, 11, k)
+    foc = g.integers(0, 2, k)
+    return wav, start.astype(np.int64), end.astype(np.int64), cat.astype(np.int64), foc.astype(np.int64)
+
+
+def _write_dataset(tmp_path, g):
+    import wave
+
+    root = tmp_path / "data" / "wav"
+    (tmp_path / "data" / "lbl").mkdir(parents=True)
+    root.mkdir(parents=True)
+    lines = [str(tmp_path / "data")]  # root above the wav/ directory, names relative to it (nn/audio_tasks.py:225-235)
+    clips = []
+    for i in range(int(g["n_clips"])):
+        wav, s, e, c, f = _synth_clip(int(g[f"seed{i}"]), int(g[f"n{i}"]))
+        pcm = np.clip(np.round(wav * 32768.0), -32768, 32767).astype("<i2")
+        with wave.open(str(root / f"c{i}.wav"), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(8000); w.writeframes(pcm.tobytes())
+        np.savez(tmp_path / "data" / "lbl" / f"c{i}.npz", start_frame_lbl=s, end_frame_lbl=e, lbl_cat=c, foc=f)
+        lines.append(f"wav/c{i}.wav\t{len(wav)}")
+        clips.append((pcm.astype(np.float32) / 32768.0, s, e, c, f))
+    (tmp_path / "train.tsv").write_text("\n".join(lines) + "\n")
+    return clips
+
+
+def test_dataset_frame_targets_match_the_reference_dataset(tmp_path):
+    """Manifest + wav + label files -> per-clip layer norm + frame-level multi-hot targets, against the output of the
+    reference's own FileAudioLabelDataset.__getitem__ (tests/golden/labels.npz, make_golden_labels.py)."""
+    from animal2vec_b200 import audio_tasks as AT
+
+    g = np.load(os.path.join(GOLD, "labels.npz"))
+    labels = [str(x) for x in g["labels"]]
+    clips = _write_dataset(tmp_path, g)
+    cfg = AT.AudioConfigCCAS(data=str(tmp_path), normalize=True, with_labels=True, unique_labels=str(labels),
+                             conv_feature_layers=str(g["conv"]), min_sample_size=1000)
+    task = AT.AudioTaskCCAS.setup_task(cfg)
+    ds = task.load_dataset("train", label_ext="npz")
+    assert len(ds) == int(g["n_clips"]) and ds.sizes.tolist() == [int(g[f"n{i}"]) for i in range(len(ds))]
+    for i in range(len(ds)):
+        item = ds[i]
+        shape = tuple(int(v) for v in g[f"target_shape{i}"])
+        want = np.unpackbits(g[f"target{i}"], axis=1)[:, : shape[1]].astype(np.int64)
+        assert item["target"].shape == shape and np.array_equal(item["target"], want), i
+        assert AT.feature_frames(int(g[f"n{i}"]), ds.conv_feature_layers) == shape[0]
+        # 16-bit PCM quantisation of the synthetic clip is the only difference from the golden float samples
+        assert np.allclose(item["source"][:64].numpy(), g[f"source_head{i}"], atol=2e-3)
+        assert abs(float(item["source"].double().sum())) < 1e-2 and \
+            abs(float(item["source"].double().pow(2).sum()) - float(g[f"source_sq{i}"])) < 1e-3 * float(g[f"source_sq{i}"])
+    batch = ds.collater([ds[0], ds[1]])
+    assert batch["net_input"]["source"].shape == (2, 80000) and batch["target"].shape == (2, 2000, 12)
+    assert batch["ntokens"] == 4000 and batch["id"].tolist() == [0, 1]
+    with pytest.raises(NotImplementedError):
+        ds.collater([ds[0], ds[2]])  # unequal clip lengths (random crops) are not on this path
+    from animal2vec_b200 import registry
+    assert registry.TASKS["audio_ccas"] is AT.AudioTaskCCAS and registry.DATACLASSES["audio_ccas"] is AT.AudioConfigCCAS
