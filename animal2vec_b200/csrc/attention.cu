@@ -487,6 +487,18 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
     const int n_mt = L > 128 ? 2 : 1;
     const int n_kt = n_mt;
     const int heads_total = p.batch * p.H;
+    // Work distribution. With the fused qkv-bias gradient (p.dbias) every CTA keeps ONE head index h for its whole life
+    // (CTA c: h = c % H, sequences b = c / H, c / H + n_h, ...), so the column sums of its 3 x 64 dqkv columns
+    // accumulate in 192 shared-memory floats and reach global memory once per CTA instead of once per row.
+    int first_head = blockIdx.x, head_step = gridDim.x;
+    if (p.dbias != nullptr) {
+        const int hf = blockIdx.x % p.H;
+        const int n_h = ((int)gridDim.x - hf + p.H - 1) / p.H;  // CTAs that share this head index
+        first_head = (blockIdx.x / p.H) * p.H + hf;
+        head_step = n_h * p.H;
+    }
+    __shared__ float s_bias[3 * HD];
+    if (tid < 3 * HD) s_bias[tid] = 0.f;
 
     if (tid == 0) {
         mbar_init(bar_load, 1);
@@ -560,8 +572,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                     tma_load_3d(smem + BT_SM_O + 16384, &tmO32, bar_load, h * HD, 128, b);
                 }
             };
-            if ((int)blockIdx.x < heads_total) load_head(blockIdx.x);
-            for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+            if (first_head < heads_total) load_head(first_head);
+            for (int head = first_head; head < heads_total; head += head_step, ++it) {
                 BT_TR(0);
                 mbar_wait_sleep(bar_load, it & 1);
                 tc_fence_after();
@@ -614,7 +626,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                     BT_TR(7 + 5 * m);
                     if (m == n_mt - 1) {  // operands free once every product of this head has retired
                         mbar_wait_sleep(bar_free, ph_tile);
-                        if (head + (int)gridDim.x < heads_total) load_head(head + gridDim.x);
+                        if (head + head_step < heads_total) load_head(head + head_step);
                         BT_TR(13);
                     }
                     ph_tile ^= 1;
@@ -649,8 +661,8 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             nx_lse0 = rt < L ? p.lse[(long long)head * L + rt] * LOG2E : 0.f;
             nx_lse1 = (n_mt > 1 && 128 + rt < L) ? p.lse[(long long)head * L + 128 + rt] * LOG2E : 0.f;
         };
-        prefetch_head(blockIdx.x);
-        for (int head = blockIdx.x; head < heads_total; head += gridDim.x, ++it) {
+        prefetch_head(first_head);
+        for (int head = first_head; head < heads_total; head += head_step, ++it) {
             const int b = head / p.H, h = head - b * p.H;
             const long long bh = head;
             const float coef = head_coef(p, h);
@@ -659,7 +671,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
             if (tid == 0) BT_TR(16);
             if (tid < BT_NK) s_pos[tid] = nx_pos;
             const float lse_m[2] = {nx_lse0, nx_lse1};
-            prefetch_head(head + gridDim.x);
+            prefetch_head(head + head_step);
             // delta_i = dO_i . O_i of both row tiles from the TMA-staged tiles (each thread: its 16 of the 64 dims)
             mbar_wait_sleep(bar_load, it & 1);
             float delta_m[2] = {0.f, 0.f};
@@ -833,6 +845,13 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                             *reinterpret_cast<uint4*>(o + d) = v;
                         }
                     }
+                    if (p.dbias != nullptr) {  // column sums of this warp's 32 rows x 16 dQ columns
+                        float cv[16];
+#pragma unroll
+                        for (int d = 0; d < 16; ++d) cv[d] = row_ok ? __uint_as_float(raw[d]) * p.sm_scale : 0.f;
+                        const float cs = warp_colsum<16>(cv, lane);
+                        if (lane < 16) atomicAdd(&s_bias[qtr * 16 + lane], cs);
+                    }
                 }
                 tc_fence_before();
                 if (tid == 0) BT_TR(24 + 8 * m);
@@ -864,6 +883,14 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
                                 *reinterpret_cast<uint4*>(o + d) = v;
                             }
                         }
+                        if (p.dbias != nullptr) {  // column sums of this warp's 32 key rows x 32 dK / dV columns
+                            const float sc = which == 0 ? p.sm_scale : 1.0f;
+                            float cv[32];
+#pragma unroll
+                            for (int d = 0; d < 32; ++d) cv[d] = j < L ? __uint_as_float(raw[d]) * sc : 0.f;
+                            const float cs = warp_colsum<32>(cv, lane);
+                            atomicAdd(&s_bias[(which + 1) * HD + c * 32 + lane], cs);
+                        }
                     }
                 }
             }
@@ -879,6 +906,10 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (p.dbias != nullptr && tid < 3 * HD && first_head < heads_total) {
+        const int hf = blockIdx.x % p.H;
+        atomicAdd(p.dbias + (tid / HD) * D + hf * HD + (tid % HD), s_bias[tid]);
+    }
     if (warp == BT_CTRL_WARP) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
@@ -1043,6 +1074,7 @@ int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
     p.qk_bound = d->qk_bound;
     p.delta = nullptr;
     p.dq_acc = nullptr;
+    p.dbias = nullptr;
     return A2V_OK;
 }
 
@@ -1163,6 +1195,10 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
     A2V_REQUIRE(p.L <= BWD_LMAX,
                 "attention backward (bf16): the shared-memory-resident kernel supports at most %d tokens per "
                 "sequence, got %d", BWD_LMAX, p.L);
+    if (d->dqkv_colsum != nullptr) {
+        A2V_REQUIRE(p.H <= a2v_num_sms(), "attention backward: fused qkv-bias gradient needs H <= number of SMs");
+        p.dbias = d->dqkv_colsum;
+    }
     static EncodeTiledFn2 encode = nullptr;
     if (encode == nullptr) {
         void* sym = nullptr;

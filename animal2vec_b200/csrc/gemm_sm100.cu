@@ -28,7 +28,7 @@ struct GemmParams {
     int kb_per_tap, taps, batch, groups;
     int m_tiles, n_tiles;
     int a_group_stride, a_row_off, a_tap_rows, a_tap_cols;
-    int a_tap_wrap, a_grow_add, a_grow_div;  // strided-conv addressing (see a2v_gemm_desc)
+    int a_tap_wrap, a_grow_add, a_grow_div, a_tap_col_stride;  // strided / gathered conv addressing (see a2v_gemm_desc)
     int b_group_stride, b_row_off, b_tap_rows;
     int red_rows, kb_per_batch, k_splits;
     void* c;
@@ -291,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const int q = tap + p.a_row_off;
                             const int rq = q >= 0 ? q / p.a_tap_wrap : -((-q + p.a_tap_wrap - 1) / p.a_tap_wrap);
                             arow = t.m_tile * BLOCK_M + rq;
-                            acol += (q - rq * p.a_tap_wrap) * p.a_tap_cols;
+                            acol += (q - rq * p.a_tap_wrap) * p.a_tap_col_stride;
                         }
                         if (p.a_grow_div > 0) arow += (t.g + p.a_grow_add) / p.a_grow_div;
                         tma_load_3d(sa, &tmA, &full_bar[stage], acol, arow, t.b);
@@ -313,7 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 const int q = tap + p.a_row_off;
                                 const int rq = q >= 0 ? q / p.a_tap_wrap : -((-q + p.a_tap_wrap - 1) / p.a_tap_wrap);
                                 arow = r0 + rq;
-                                acol += (q - rq * p.a_tap_wrap) * p.a_tap_cols;
+                                acol += (q - rq * p.a_tap_wrap) * p.a_tap_col_stride;
                             }
                             tma_load_3d(sa + i * (64 * BLOCK_K * 2), &tmA, &full_bar[stage], acol, arow, b);
                         }
@@ -749,6 +749,7 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
     p.a_tap_wrap = d->a_tap_wrap;
     p.a_grow_add = d->a_grow_add;
     p.a_grow_div = d->a_grow_div;
+    p.a_tap_col_stride = d->a_tap_col_stride > 0 ? d->a_tap_col_stride : d->a_tap_cols;
     p.b_group_stride = d->b_group_stride;
     p.b_row_off = d->b_row_off;
     p.b_tap_rows = d->b_tap_rows;
@@ -780,8 +781,8 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         if ((rc = make_map(&ta, d->a, BLOCK_M, "A")) != A2V_OK) return rc;
         if ((rc = make_map(&tb, d->b, d->block_n, "B")) != A2V_OK) return rc;
         A2V_REQUIRE(d->a_tap_cols == 0 || d->a_tap_wrap > 0, "gemm: NT mode takes a_tap_cols only with a_tap_wrap (strided conv)");
-        A2V_REQUIRE(d->a_tap_wrap == 0 || (d->a_tap_cols > 0 && d->a_tap_cols % 8 == 0 && d->a_tap_cols == d->k_per_tap),
-                    "gemm: strided conv needs a_tap_cols == k_per_tap (channels per input row)");
+        A2V_REQUIRE(d->a_tap_wrap == 0 || (d->a_tap_cols > 0 && d->a_tap_cols % 8 == 0 && d->a_tap_col_stride % 8 == 0),
+                    "gemm: wrapped tap addressing needs a_tap_cols / a_tap_col_stride in multiples of 8 columns");
     } else {
         A2V_REQUIRE(d->red_rows > 0 && d->k_splits >= 1, "gemm: TN mode needs red_rows > 0 and k_splits >= 1");
         A2V_REQUIRE(d->k_splits == 1 || d->out_atomic, "gemm: split-K requires out_atomic");

@@ -167,6 +167,17 @@ __global__ void __launch_bounds__(256) clone_sum_bwd_kernel(const T* __restrict_
     }
 }
 
+__global__ void __launch_bounds__(256) neigh_index_kernel(const int* __restrict__ ids_keep, long long n, int Tk, int T_,
+                                                          int taps, int pad, int* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        const long long tok = e / taps;
+        const int j = (int)(e - tok * taps);
+        const long long r = tok / Tk;
+        const int t = ids_keep[tok] + j - pad;
+        out[e] = (t >= 0 && t < T_) ? (int)(r * T_ + t) : -1;
+    }
+}
+
 static int grid_for_rows(long long rows) {
     long long b = ceil_div64(rows, 8);
     long long cap = (long long)a2v_num_sms() * 16;
@@ -189,6 +200,19 @@ extern "C" int a2v_mask_index(const uint8_t* mask, int rows, int T, int Tk, int 
     mask_index_kernel<<<rows, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         mask, T, Tk, clones, ids_keep, ids_restore, clone_src, keep_src_x, keep_src_clone, restore_src, err_flag);
     return a2v_check_launch("mask_index");
+}
+
+extern "C" int a2v_neigh_index(const int32_t* ids_keep, int rows, int Tk, int T, int taps, int pad, int32_t* out,
+                               a2v_stream_t stream) {
+    A2V_REQUIRE(ids_keep && out && rows >= 0 && Tk >= 0 && T > 0 && taps >= 1 && pad >= 0, "neigh_index: bad arguments");
+    A2V_REQUIRE((long long)rows * T < (1LL << 31), "neigh_index: rows*T must fit int32 row maps");
+    const long long n = (long long)rows * Tk * taps;
+    if (n == 0) return A2V_OK;
+    long long blocks = ceil_div64(n, 256);
+    const long long cap = (long long)a2v_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    neigh_index_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ids_keep, n, Tk, T, taps, pad, out);
+    return a2v_check_launch("neigh_index");
 }
 
 extern "C" int a2v_row_gather(int dtype, const void* src, const int32_t* idx, const void* add, void* dst,

@@ -138,6 +138,8 @@ class PretrainEngine:
         self.kernel_launches = 0
         self.has_teacher = True
         self.has_decoder = True
+        # bf16: the last positional-conv layer of the student runs on the kept rows only (see _posconv_forward)
+        self.sparse_last_posconv = True
 
     # ------------------------------------------------------------------------------------ support matrix
     @staticmethod
@@ -477,17 +479,34 @@ class PretrainEngine:
             c.proj = SimpleNamespace(lnp=lnp, m=m, r=r, cfg=cfgp, a=fe[-1].a)
         return lf
 
-    def _posconv_forward(self, W: _Weights, x: torch.Tensor, save: Optional[list]) -> torch.Tensor:
-        """audio.py:93-113: depth x [grouped Conv1d(k, pad k//2) + bias, LN(no affine), GELU]."""
+    def _posconv_forward(self, W: _Weights, x: torch.Tensor, save: Optional[list], kept=None) -> torch.Tensor:
+        """audio.py:93-113: depth x [grouped Conv1d(k, pad k//2) + bias, LN(no affine), GELU].
+
+        ``kept`` (a MaskIndex, bf16 student path): only the kept positions of the LAST layer's output are ever read
+        (base.py:278-280 gathers x_pos at ids_keep), so that layer -- conv, LayerNorm, GELU and in the backward its
+        LayerNorm and weight gradient -- runs on the R*Tk kept rows instead of all R*T: the +-k/2 neighbourhood of every
+        kept frame is gathered into a (rows, taps, D) operand and the grouped conv becomes one tap-blocked GEMM. Returns
+        (R*Tk, D) in kept-row order then, (R, T, D) otherwise."""
         if self.kp % 2 == 0:
             raise NotImplementedError("even positional-conv kernel (SamePad trim)")
         g = self.a.conv_pos_groups
         cfg_l = ops.RowLnCfg(self.D, 1e-5, act=1)
-        for n in self.pos_names:
-            y = self.conv(x, W, n, taps=self.kp, pad=self.kp // 2, groups=g, bias=W.f32[n[:-6] + "bias"])
+        last = len(self.pos_names) - 1
+        for li, n in enumerate(self.pos_names):
+            bias = W.f32[n[:-6] + "bias"]
+            if kept is not None and li == last:
+                rows, t = x.shape[0], x.shape[1]
+                nidx = ops.neigh_index(kept.ids_keep, t, self.kp, self.kp // 2)
+                xg = ops.row_gather(x.view(rows * t, self.D), nidx, nidx.numel()).view(-1, self.kp, self.D)
+                y = gemm.gathered_conv_nt(xg, W.fwd[n], taps=self.kp, groups=g, bias=bias, out_dtype=self.adt)
+                act, m, r = ops.rowln_fwd(cfg_l, y, save_stats=save is not None)
+                if save is not None:
+                    save.append(SimpleNamespace(xg=xg, y=y, m=m, r=r, sparse=True))
+                return act
+            y = self.conv(x, W, n, taps=self.kp, pad=self.kp // 2, groups=g, bias=bias)
             act, m, r = ops.rowln_fwd(cfg_l, y, save_stats=save is not None)
             if save is not None:
-                save.append(SimpleNamespace(x=x, y=y, m=m, r=r))
+                save.append(SimpleNamespace(x=x, y=y, m=m, r=r, sparse=False))
             x = act
         return x
 
@@ -604,9 +623,13 @@ class PretrainEngine:
         lf2 = lf.view(B * T, d)
         x_masked = ops.row_gather(lf2, mi.clone_src, R * T, out_shape=(R, T, d))
         c.pos = [] if save else None
-        x_pos = self._posconv_forward(self.WS, x_masked, c.pos)
+        sparse_last = self.sparse_last_posconv and not self.fp32 and (d // self.a.conv_pos_groups) % 64 == 0
+        x_pos = self._posconv_forward(self.WS, x_masked, c.pos, kept=mi if sparse_last else None)
         x_unm = ops.row_gather(lf2, mi.keep_src_x, R * tk, out_shape=(R * tk, d))
-        xs = ops.row_gather(x_pos.view(R * T, d), mi.keep_src_clone, R * tk, add=x_unm, out_shape=(R * tk, d))
+        if sparse_last:  # x_pos is already (R*Tk, D) in kept-row order
+            xs = self._add(x_pos, x_unm)
+        else:
+            xs = ops.row_gather(x_pos.view(R * T, d), mi.keep_src_clone, R * tk, add=x_unm, out_shape=(R * tk, d))
         del x_pos, x_unm, x_masked
         c.blocks = [] if save else None
         xs = self._encoder_forward(self.WS, xs, R, tk, mi.ids_keep, training, c.blocks, None, c)
@@ -740,8 +763,8 @@ class PretrainEngine:
         dal = G(ENC + "alibi_scale").view(-1) if self.a.learned_alibi_scale else None
         dqkv = ops.attn_bwd(dao.view(rows, seq, self.D), s.qkv.view(rows, seq, 3 * self.D), s.ao, s.lse, rows, seq,
                             self.H, pos=pos, slopes=self.slopes, alibi_scale=W.alibi, dalibi_scale=dal,
-                            drop_p=s.p_att, seed=s.s_att).view(rows * seq, 3 * self.D)
-        ops.colsum(dqkv, G(pre + "attn.qkv.bias"))
+                            drop_p=s.p_att, seed=s.s_att,
+                            dqkv_colsum=G(pre + "attn.qkv.bias")).view(rows * seq, 3 * self.D)
         self.wgrad(dqkv, s.x, G(pre + "attn.qkv.weight"))
         return self.lin(dqkv, W, pre + "attn.qkv.weight", dgrad=True, residual=dz1)
 
@@ -795,12 +818,22 @@ class PretrainEngine:
                                training=training, dgamma=G(ENC + "context_encoder.norm.weight"),
                                dbeta=G(ENC + "context_encoder.norm.bias"))
         # xs0 = x_unmasked + x_pos[ids_keep]
-        dpos = ops.row_gather(dxs, mi.restore_src, R * T, out_shape=(R, T, d))
         g = self.a.conv_pos_groups
         cfg_l = ops.RowLnCfg(d, 1e-5, act=1)
+        dpos = None
         for li in reversed(range(len(self.pos_names))):
             s = c.pos[li]
             n = self.pos_names[li]
+            if s.sparse:  # last layer, evaluated on the kept rows only (see _posconv_forward)
+                dyk, _ = ops.rowln_bwd(cfg_l, dxs, s.y, None, None, None, None, None, s.m, s.r)
+                ops.colsum(dyk, G(n[:-6] + "bias"))
+                gemm.gathered_conv_wgrad_tn(dyk, s.xg, self.gpacked[n + "|F"], taps=self.kp, groups=g)
+                dy = ops.row_gather(dyk, mi.restore_src, R * T, out_shape=(R, T, d))  # zeros at the masked frames
+                dpos = self.conv(dy, W, n, taps=self.kp, pad=self.kp - 1 - self.kp // 2, groups=g, dgrad=True)
+                c.pos[li] = None
+                continue
+            if dpos is None:
+                dpos = ops.row_gather(dxs, mi.restore_src, R * T, out_shape=(R, T, d))
             dy, _ = ops.rowln_bwd(cfg_l, dpos, s.y, None, None, None, None, None, s.m, s.r)
             ops.colsum(dy.view(R * T, d), G(n[:-6] + "bias"))
             self.conv_wgrad(dy, s.x, self.gpacked[n + "|F"], taps=self.kp, pad=self.kp // 2, groups=g)

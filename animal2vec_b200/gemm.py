@@ -274,6 +274,73 @@ def strided_conv_wgrad_tn(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, 
     return out
 
 
+def gathered_conv_nt(xg: torch.Tensor, w: torch.Tensor, *, taps: int, groups: int, bias: Optional[torch.Tensor] = None,
+                     out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Grouped conv evaluated only at pre-gathered positions. ``xg``: (M, taps, C) bf16 (row m, tap j = input frame
+    pos_m + j - pad, zeros outside the sequence), ``w``: (G*Ng, taps*Cg) tap-major (params.pack_conv_fwd):
+        y[m, g*Ng + n] = bias + sum_{j, c} xg[m, j, g*Cg + c] * w[g*Ng + n, j*Cg + c]."""
+    m, taps_, c = xg.shape
+    assert taps_ == taps and xg.is_contiguous() and w.is_contiguous()
+    cg = c // groups
+    nout = w.shape[0]
+    ng = nout // groups
+    assert w.shape[1] == taps * cg and cg % 64 == 0
+    out = torch.empty(m, nout, device=xg.device, dtype=out_dtype or torch.bfloat16)
+    d = L.GemmDesc()
+    d.mode = 0
+    d.block_n = _pick_block_n(ng)
+    d.a = _operand(xg, taps * c, m, 1, taps * c, 0)
+    d.b = _operand(w, taps * cg, nout, 1, taps * cg, 0)
+    d.M, d.N, d.k_per_tap, d.taps, d.batch, d.groups = m, ng, cg, taps, 1, groups
+    d.a_group_stride, d.a_row_off, d.a_tap_rows = cg, 0, 0
+    d.a_tap_cols, d.a_tap_wrap, d.a_tap_col_stride = cg, taps, c
+    d.b_group_stride = ng
+    d.k_splits = 1
+    d.c = out.data_ptr()
+    d.c_dtype = L.dtype_code(out)
+    d.ldc = nout
+    d.c_group_stride = ng
+    d.alpha = 1.0
+    d.bias = bias.data_ptr() if bias is not None else None
+    _launch(d, xg)
+    return out
+
+
+def gathered_conv_wgrad_tn(dy: torch.Tensor, xg: torch.Tensor, out: torch.Tensor, *, taps: int, groups: int,
+                           k_splits: Optional[int] = None) -> torch.Tensor:
+    """Weight gradient of :func:`gathered_conv_nt` in the transposed tap-major layout of conv_wgrad_tn:
+    out[(g*taps + j)*Cg + c, n] += sum_m xg[m, j, g*Cg + c] * dy[m, g*Ng + n]   (fp32, atomically accumulated)."""
+    m, taps_, c = xg.shape
+    nout = dy.shape[-1]
+    cg, ng = c // groups, nout // groups
+    assert taps_ == taps and dy.shape[0] == m and dy.is_contiguous() and xg.is_contiguous() and cg % 64 == 0
+    assert out.dtype == torch.float32 and out.shape == (groups * taps * cg, ng) and out.is_contiguous()
+    d = L.GemmDesc()
+    d.mode = 1
+    d.block_n = 64 if ng <= 64 else (128 if ng <= 128 else 256)
+    d.a = _operand(xg, taps * c, m, 1, taps * c, 0)
+    d.b = _operand(dy, nout, m, 1, nout, 0)
+    d.M, d.N, d.taps, d.batch, d.groups = taps * cg, ng, 1, 1, groups
+    d.a_group_stride, d.a_row_off, d.a_tap_rows = cg, 0, 0
+    d.a_tap_cols, d.a_tap_wrap, d.a_tap_col_stride = cg, taps, c
+    d.b_group_stride, d.b_row_off, d.b_tap_rows = ng, 0, 0
+    d.red_rows = m
+    tiles = -(-(taps * cg) // 128) * -(-ng // d.block_n) * groups
+    kblocks = -(-m // 64)
+    ks = k_splits or (_pick_splits(tiles, kblocks) if tiles < 148 else _pick_splits_waves(tiles, kblocks))
+    per = -(-kblocks // ks)
+    d.k_splits = -(-kblocks // per)
+    d.c = out.data_ptr()
+    d.c_dtype = L.F32
+    d.out_atomic = 1
+    d.ldc = ng
+    d.c_group_stride = taps * cg
+    d.c_tap_stride = 0
+    d.alpha = 1.0
+    _launch(d, xg)
+    return out
+
+
 def conv_slab_ok(x: torch.Tensor, w: torch.Tensor, taps: int, groups: int) -> bool:
     """The slab kernel covers bf16 tap convs with 64-channel groups and <= 64 outputs per group."""
     if x.dtype != torch.bfloat16 or x.dim() != 3 or taps > 32:
@@ -348,6 +415,21 @@ def conv_slab_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, tap
     else:
         fn()
     return out
+
+
+def _pick_splits_waves(tiles: int, kblocks: int, max_splits: int = 8) -> int:
+    """Split count for tile counts slightly above the SM count: the split that wastes the least of its last wave
+    (160 tiles on 148 SMs run as two waves with the second 8 % full; 7 splits fill 7.6 of 8 waves)."""
+    sms = 148
+    best, best_eff = 1, 0.0
+    for s_ in range(1, max_splits + 1):
+        if kblocks // s_ < 8:
+            break
+        work = tiles * s_
+        eff = work / (-(-work // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s_, eff
+    return best
 
 
 def _pick_splits(tiles: int, kblocks: int) -> int:

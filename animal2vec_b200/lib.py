@@ -89,6 +89,7 @@ class GemmDesc(C.Structure):
         ("a_tap_wrap", C.c_int),
         ("a_grow_add", C.c_int),
         ("a_grow_div", C.c_int),
+        ("a_tap_col_stride", C.c_int),
     ]
 
 

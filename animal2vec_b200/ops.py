@@ -70,6 +70,7 @@ class AttnDesc(C.Structure):
         ("bwd_algo", C.c_int),
         ("workspace", C.c_void_p),
         ("workspace_bytes", C.c_int64),
+        ("dqkv_colsum", C.c_void_p),
     ]
 
 
@@ -213,7 +214,7 @@ BWD_RESIDENT_MAX = 160  # tokens per sequence the shared-memory-resident backwar
 
 
 def attn_bwd(dout, qkv, out, lse, batch, seq, heads, *, pos=None, slopes=None, alibi_scale=None,
-             dalibi_scale=None, drop_p=0.0, seed=0, algo=0, skip_far_keys=True):
+             dalibi_scale=None, drop_p=0.0, seed=0, algo=0, skip_far_keys=True, dqkv_colsum=None):
     """``algo``: 0 automatic (bf16: resident kernel up to 160 tokens, tiled kernel beyond), 1 resident, 2 tiled.
     The tiled kernel runs as prepare -> backward -> finish (three launches) over a workspace allocated here."""
     assert dout.is_contiguous() and dout.dtype == qkv.dtype
@@ -239,12 +240,19 @@ def attn_bwd(dout, qkv, out, lse, batch, seq, heads, *, pos=None, slopes=None, a
     d.sm_scale = 64 ** -0.5
     d.drop_p, d.seed = drop_p, seed
     d.dout, d.dqkv, d.dalibi_scale = _p(dout), _p(dqkv), _p(dalibi_scale)
+    fuse_colsum = (dqkv_colsum is not None and not tiled and qkv.dtype == torch.bfloat16 and seq <= BWD_RESIDENT_MAX
+                   and heads <= 128)
+    if fuse_colsum:  # qkv-bias gradient accumulated inside the resident kernel
+        assert dqkv_colsum.dtype == torch.float32 and dqkv_colsum.numel() == 3 * heads * 64
+        d.dqkv_colsum = _p(dqkv_colsum)
     if tiled:
         _call("a2v_attn_bwd_prepare", qkv, C.byref(d))
         _call("a2v_attn_bwd", qkv, C.byref(d))
         _call("a2v_attn_bwd_finish", qkv, C.byref(d))
-        return dqkv
-    _call("a2v_attn_bwd", qkv, C.byref(d))
+    else:
+        _call("a2v_attn_bwd", qkv, C.byref(d))
+    if dqkv_colsum is not None and not fuse_colsum:
+        colsum(dqkv.view(-1, dqkv.shape[-1]), dqkv_colsum)
     return dqkv
 
 
@@ -286,6 +294,15 @@ def row_gather(src, idx, n_dst, *, add=None, fill_std=0.0, fill_seed=0, drop_p=0
     _call("a2v_row_gather", src, L.dtype_code(src), _p(src), _p(idx), _p(add), _p(dst), C.c_int64(n_dst), d_,
           C.c_float(fill_std), C.c_uint64(fill_seed), C.c_float(drop_p), C.c_uint64(drop_seed), int(drop_by_src))
     return dst
+
+
+def neigh_index(ids_keep: torch.Tensor, t: int, taps: int, pad: int) -> torch.Tensor:
+    """(rows*Tk*taps,) int32 row map: flat row r*T + ids_keep[r, i] + j - pad of the (rows*T, C) activation, -1 outside."""
+    rows, tk = ids_keep.shape
+    assert ids_keep.dtype == torch.int32 and ids_keep.is_contiguous()
+    out = torch.empty(rows * tk * taps, device=ids_keep.device, dtype=torch.int32)
+    _call("a2v_neigh_index", ids_keep, _p(ids_keep), rows, tk, t, taps, pad, _p(out))
+    return out
 
 
 def clone_sum_bwd(d_masked, d_unmasked, restore_src, b, t, clones, d_):

@@ -108,6 +108,11 @@ typedef struct {
     int a_tap_wrap;
     int a_grow_add;
     int a_grow_div;
+    /* column distance between consecutive column blocks of the wrapped tap addressing when it differs from a_tap_cols
+     * (0 = a_tap_cols). Gathered convolution: rows pre-gathered as (M, taps, C) -- A viewed (M, taps*C), a_tap_wrap = taps,
+     * a_row_off = 0, a_tap_col_stride = C, groups select 64-channel slices inside each tap block (the last positional-conv
+     * layer evaluated only on the rows the student keeps, nn/modalities/base.py:278-280). */
+    int a_tap_col_stride;
 } a2v_gemm_desc;
 
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);
@@ -214,6 +219,10 @@ int a2v_row_gather(int dtype, const void* src, const int32_t* idx, const void* a
                    a2v_stream_t stream);
 int a2v_clone_sum_bwd(int dtype, const void* d_masked, const void* d_unmasked, const int32_t* restore_src,
                       void* dx, int64_t B, int T, int clones, int D, a2v_stream_t stream);
+/* Neighbourhood row map of the kept tokens: out[(r * Tk + i) * taps + j] = r * T + ids_keep[r, i] + j - pad, or -1 when
+ * that frame lies outside [0, T) (zero padding of the conv). Feeds a2v_row_gather to build the (rows, taps, C) operand of a
+ * convolution evaluated only at the kept positions. */
+int a2v_neigh_index(const int32_t* ids_keep, int rows, int Tk, int T, int taps, int pad, int32_t* out, a2v_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Teacher targets and masked regression loss (HBM-bound).
@@ -346,6 +355,10 @@ typedef struct {
     int bwd_algo;
     void* workspace;
     int64_t workspace_bytes;
+    /* backward, optional, bf16 resident kernel only (L <= 160): fp32 (3 * H * 64) vector that receives += the column sums
+     * of dqkv, i.e. the gradient of the qkv Linear's bias (nn/modalities/modules.py:371), accumulated per CTA in shared
+     * memory instead of by a separate pass over dqkv. Other kernels reject it (use a2v_colsum). */
+    float* dqkv_colsum;
 } a2v_attn_desc;
 
 int a2v_attn_qk_bound(const void* qkv_bf16, float* bound, int batch, int L, int H, a2v_stream_t stream);

@@ -214,3 +214,42 @@ def test_strided_conv_without_im2col(bsz, t, c, c_real, n, k, s, pad):
     got = torch.zeros_like(w)
     P.unpack_grad(pk_f, gw, got, transposed=True)
     assert _rel(got, wr.grad) < 6e-3, _rel(got, wr.grad)
+
+
+@pytest.mark.parametrize("rows,t,tk,groups,taps", [(6, 300, 23, 2, 19), (24, 2000, 148, 16, 19), (3, 130, 130, 4, 7)])
+def test_gathered_conv_on_kept_rows(rows, t, tk, groups, taps):
+    """The last positional-conv layer evaluated only at the kept positions: neighbourhood row map + row gather +
+    tap-blocked grouped GEMM (forward) and its weight gradient, against F.conv1d over the full sequence read at the kept
+    rows / autograd with a gradient that is zero elsewhere."""
+    from animal2vec_b200 import gemm, ops
+    from animal2vec_b200 import params as P
+
+    c = groups * 64
+    pad = taps // 2
+    x = _randn(rows, t, c, seed=1)
+    w = _randn(c, 64, taps, scale=0.05, seed=2).float()
+    bias = _randn(c, seed=3).float()
+    g = torch.Generator().manual_seed(4)
+    ids = torch.stack([torch.randperm(t, generator=g)[:tk].sort().values for _ in range(rows)]).to(torch.int32).cuda()
+    pk = P.pack_conv_fwd("w", groups, 64, 64, taps)
+    wf = P.materialize(pk, w, False)
+    nidx = ops.neigh_index(ids, t, taps, pad)
+    ref_idx = (torch.arange(rows, device="cuda")[:, None, None] * t + ids.long()[:, :, None]
+               + torch.arange(taps, device="cuda")[None, None, :] - pad)
+    inside = (ids.long()[:, :, None] + torch.arange(taps, device="cuda") - pad >= 0) & \
+             (ids.long()[:, :, None] + torch.arange(taps, device="cuda") - pad < t)
+    assert torch.equal(nidx.view(rows, tk, taps).long(), torch.where(inside, ref_idx, torch.full_like(ref_idx, -1)))
+    xg = ops.row_gather(x.view(rows * t, c), nidx, nidx.numel()).view(rows * tk, taps, c)
+    y = gemm.gathered_conv_nt(xg, wf, taps=taps, groups=groups, bias=bias)
+    xr = x.float()
+    wr = w.clone().requires_grad_(True)
+    full = F.conv1d(xr.transpose(1, 2), wr, bias, padding=pad, groups=groups).transpose(1, 2)  # (rows, t, c)
+    ref = torch.gather(full, 1, ids.long().unsqueeze(-1).expand(-1, -1, c)).reshape(rows * tk, c)
+    assert _rel(y, ref) < 6e-3, _rel(y, ref)
+    dy = _randn(rows * tk, c, seed=5)
+    ref.backward(dy.float())
+    gw = torch.zeros(pk.gt_shape, device="cuda")
+    gemm.gathered_conv_wgrad_tn(dy, xg, gw, taps=taps, groups=groups)
+    got = torch.zeros_like(w)
+    P.unpack_grad(pk, gw, got, transposed=True)
+    assert _rel(got, wr.grad) < 6e-3, _rel(got, wr.grad)

@@ -183,6 +183,29 @@ def test_attention_fwd_bwd(dtype, batch, seq, heads, with_pos):
         assert _rel(dsc, sr.grad) < max(gt, 1e-3), (dsc, sr.grad)
 
 
+@pytest.mark.parametrize("batch,seq,heads", [(5, 148, 16), (300, 142, 4), (2, 97, 2), (1, 129, 3)])
+def test_attention_backward_fused_qkv_bias_gradient(batch, seq, heads):
+    """The resident backward accumulates the column sums of dqkv (= the qkv bias gradient) per CTA in shared memory;
+    must equal the separate column-sum pass over the stored dqkv, for grids smaller and larger than the SM count."""
+    from animal2vec_b200 import ops
+
+    d = heads * 64
+    qkv = torch.randn(batch, seq, 3 * d, device="cuda", generator=_g(1)).bfloat16()
+    pos = torch.stack([torch.randperm(2000, device="cuda", generator=_g(10 + i % 7))[:seq].sort().values
+                       for i in range(batch)]).to(torch.int32).contiguous()
+    slopes = torch.tensor([2.0 ** (-8.0 * (h + 1) / heads) for h in range(heads)], device="cuda")
+    scale = torch.ones(heads, device="cuda")
+    out, lse = ops.attn_fwd(qkv, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=0.1, seed=5)
+    dout = torch.randn(batch, seq, d, device="cuda", generator=_g(3)).bfloat16()
+    acc = torch.full((3 * d,), 0.25, device="cuda")  # accumulates on top of what is there
+    dqkv = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=0.1,
+                        seed=5, dqkv_colsum=acc)
+    plain = ops.attn_bwd(dout, qkv, out, lse, batch, seq, heads, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=0.1, seed=5)
+    assert torch.equal(dqkv, plain)  # the work distribution (head-major vs interleaved) does not change the result
+    want = dqkv.float().view(-1, 3 * d).sum(0) + 0.25
+    assert _rel(acc, want) < 3e-3, _rel(acc, want)  # fp32 pre-rounding sums vs sums of the bf16-rounded rows
+
+
 @pytest.mark.parametrize("batch,seq,heads,with_pos,drop_p",
                          [(3, 142, 4, True, 0.0), (2, 128, 2, False, 0.0), (2, 129, 2, True, 0.1), (2, 300, 2, False, 0.0),
                           (2, 852, 4, True, 0.0), (1, 1000, 2, True, 0.2), (2, 2000, 16, False, 0.0), (1, 2100, 3, False, 0.1)])

@@ -136,7 +136,7 @@ def test_decoder_input_dropout_forward_backward_pairing(dtype):
 
 LARGE_GRAD_KEYS = [
     "blocks.0.attn.qkv.weight", "blocks.0.mlp.fc1.weight", "blocks.15.attn.qkv.weight", "blocks.15.mlp.fc1.weight",
-    "blocks.15.mlp.fc2.bias", "blocks.7.attn.proj.weight", "blocks.7.norm2.weight",
+    "blocks.15.mlp.fc2.bias", "blocks.7.attn.proj.weight", "blocks.7.norm2.weight", "blocks.3.attn.qkv.bias",
     O.ENC + "context_encoder.blocks.0.attn.qkv.weight", O.ENC + "context_encoder.blocks.7.mlp.fc2.weight",
     O.ENC + "context_encoder.norm.weight", O.ENC + "alibi_scale",
     O.ENC + "relative_positional_encoder.1.0.weight", O.ENC + "relative_positional_encoder.5.0.weight",
