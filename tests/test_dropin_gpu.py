@@ -175,3 +175,33 @@ def test_extract_features_and_remove_pretraining_modules_match_reference_fixture
     with pytest.raises(RuntimeError):
         model.train()
         model(x.cuda(), id=torch.arange(b))  # pretraining forward is gone
+
+
+def test_load_pretrained_from_a_reference_format_checkpoint():
+    """SURVEY 8f-3: {"model": state incl. "_ema" (4-D alibi_scale), "cfg": {"model": yaml node, "task": ...}} -> model;
+    same loss as an engine built from the same tensors; a diverged teacher in "_ema" is honoured."""
+    import dataclasses
+
+    from animal2vec_b200 import checkpoint as CK
+    from animal2vec_b200 import config as Cfg
+    from animal2vec_b200.engine import PretrainEngine
+
+    g = dict(np.load(os.path.join(GOLD, "tiny_u0.npz"), allow_pickle=False))
+    params = O.init_params(O.tiny_config(), 0)
+    node = dataclasses.asdict(Cfg.no_randomness(Cfg.tiny()))
+    node.update({"_name": "data2vec_multi", "supported_modality": "AUDIO"})
+    node["modalities"]["audio"]["type"] = "AUDIO"
+    sd = {k: v.clone() for k, v in params.items()}
+    sd[O.ENC + "alibi_scale"] = sd[O.ENC + "alibi_scale"].squeeze(0)
+    teacher = {k: v * 1.01 for k, v in O.make_teacher(params).items()}  # a teacher that has drifted from the student
+    sd["_ema"] = {k: v.clone() for k, v in teacher.items()}
+    model = CK.load_pretrained({"model": sd, "cfg": {"model": node, "task": {"sample_rate": 8000}}}, precision="fp32")
+    model.train()
+    sample = _sample(g)
+    res = model(**sample["net_input"])
+    eng = PretrainEngine(Cfg.no_randomness(Cfg.tiny()), "cuda", precision="fp32", init=params)
+    eng.load_teacher(teacher)
+    ref = eng.forward(sample["net_input"]["source"], sample["id"], 0, need_grad=False)
+    a, b = float(res["losses"]["AUDIO_regression"]), float(ref["loss_sum"])
+    assert abs(a - b) <= 1e-6 * abs(b)
+    assert abs(a - float(g["loss_sum"])) > 1e-4 * abs(a)  # the drifted teacher changes the targets

@@ -315,14 +315,15 @@ def test_fairseq_registration_hook_against_a_stub_package(tmp_path):
         import sys
         sys.path.insert(0, %r); sys.path.insert(0, %r)
         import fairseq.models as FM, fairseq.criterions as FC, fairseq.tasks as FT
-        import animal2vec_b200.data2vec2, animal2vec_b200.criterions
+        import animal2vec_b200.data2vec2, animal2vec_b200.criterions, animal2vec_b200.wav2vec2, animal2vec_b200.audio_tasks
         from animal2vec_b200 import registry
-        assert set(FM.REGISTRY) >= {"data2vec_multi"}, FM.REGISTRY
-        assert set(FC.REGISTRY) >= {"expanded_model"}, FC.REGISTRY
+        assert set(FM.REGISTRY) == {"data2vec_multi", "wav2vec_ccas_finetune"}, FM.REGISTRY
+        assert set(FC.REGISTRY) == {"expanded_model", "finetunecriterion"}, FC.REGISTRY
+        assert set(FT.REGISTRY) == {"audio_ccas"} and issubclass(FT.REGISTRY["audio_ccas"][0], FT.FairseqTask), FT.REGISTRY
         assert issubclass(FM.REGISTRY["data2vec_multi"][0], FM.BaseFairseqModel)
         assert issubclass(FC.REGISTRY["expanded_model"][0], FC.FairseqCriterion)
         assert FM.REGISTRY["data2vec_multi"][1] is registry.DATACLASSES["data2vec_multi"]
-        assert len(registry.FAIRSEQ_REGISTERED) >= 2
+        assert len(registry.FAIRSEQ_REGISTERED) == 5
         try:
             registry.register_model("data2vec_multi_x")(type("NotAModel", (), {}))   # wrong base class must surface, not be swallowed
         except ValueError as e:
@@ -398,3 +399,70 @@ def test_dataset_frame_targets_match_the_reference_dataset(tmp_path):
         ds.collater([ds[0], ds[2]])  # unequal clip lengths (random crops) are not on this path
     from animal2vec_b200 import registry
     assert registry.TASKS["audio_ccas"] is AT.AudioTaskCCAS and registry.DATACLASSES["audio_ccas"] is AT.AudioConfigCCAS
+
+
+def test_reference_checkpoint_dict_to_config_and_inventory():
+    """a trainer-format checkpoint dict ({"model": ..., "cfg": {...}}) written by the reference resolves to
+    this package's config (field names are the reference's, yaml model node of a2v_large_pretrain_best.yaml) and its
+    tensors pass the key / shape inventory, incl. the 4-D alibi_scale of old checkpoints."""
+    import dataclasses
+    import types
+
+    from animal2vec_b200 import checkpoint as CK
+    from oracle import a2v_oracle as O
+
+    base = Cfg.tiny()
+    model_node = dataclasses.asdict(base)
+    model_node["_name"] = "data2vec_multi"
+    model_node["supported_modality"] = "AUDIO"
+    model_node["modalities"]["audio"]["type"] = "AUDIO"
+    model_node["sample_rate"] = None
+    params = O.init_params(O.tiny_config(), 0)
+    sd = {k: v.clone() for k, v in params.items()}
+    sd[O.ENC + "alibi_scale"] = sd[O.ENC + "alibi_scale"].squeeze(0)  # pre-upgrade layout
+    sd["_ema"] = {k: v.clone() for k, v in O.make_teacher(params).items()}
+    state = {"model": sd, "cfg": types.SimpleNamespace(model=model_node, task={"sample_rate": 8000, "_name": "audio_ccas"})}
+    cfg = CK.model_config_from_checkpoint(state)
+    assert cfg.embed_dim == base.embed_dim and cfg.modalities.audio.prenet_depth == base.modalities.audio.prenet_depth
+    assert cfg.sample_rate == 8000 and cfg.modalities.audio.sample_rate == 8000
+    student, ema = CK.split_model_state(state)
+    assert student[O.ENC + "alibi_scale"].dim() == 5 and "_ema" not in student
+    CK.check_inventory(cfg, student, ema)
+    broken = dict(student)
+    broken.pop("blocks.0.mlp.fc1.weight")
+    with pytest.raises(KeyError):
+        CK.check_inventory(cfg, broken, ema)
+    with pytest.raises(ValueError):
+        CK.model_config_from_checkpoint({"cfg": {"model": {"_name": "wav2vec2"}}})
+
+
+def test_constructor_surface_modules_carry_the_reference_parameter_inventory():
+    """SURVEY 8b constructors (SincConv, ConvFeatureExtractionModel, AudioEncoder, AltBlock, Decoder1d): same signatures,
+    and their parameter names / shapes equal the checkpoint ABI of the modality encoder."""
+    import torch.nn as nn
+
+    from animal2vec_b200 import modules as M
+
+    cfg = Cfg.tiny()
+    a = cfg.modalities.audio
+    mk = lambda dp: M.AltBlock(cfg.embed_dim, cfg.num_heads, cfg.mlp_ratio, qkv_bias=True, drop=cfg.encoder_dropout,
+                               attn_drop=cfg.attention_dropout, mlp_drop=cfg.activation_dropout,
+                               post_mlp_drop=cfg.post_mlp_drop, drop_path=dp, norm_layer=nn.LayerNorm,
+                               layer_norm_first=cfg.layer_norm_first, ffn_targets=True)
+    enc = M.AudioEncoder(a, cfg.embed_dim, mk, nn.LayerNorm, cfg.layer_norm_first, {}, None)
+    got = {O_ENC + k: v for k, v in M.reference_state_keys(enc).items()}
+    shapes = {k: tuple(v) for k, v in P.student_param_shapes(cfg).items() if k.startswith(O_ENC)}
+    assert got == shapes, (sorted(set(got) ^ set(shapes))[:10])
+    blk = mk(0.0)
+    want = {k[len("blocks.0."):]: tuple(v) for k, v in P.student_param_shapes(cfg).items() if k.startswith("blocks.0.")}
+    assert M.reference_state_keys(blk) == want
+    sc = M.SincConv(127, 63, sample_rate=8000)
+    low, band = P.sinc_mel_init(127, 63, 8000)
+    assert torch.equal(sc.low_hz_.detach(), low) and torch.equal(sc.band_hz_.detach(), band) and sc.min_band_hz == 127
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 4, cfg.embed_dim))
+    with pytest.raises(NotImplementedError):
+        M.SincConv(127, 63, learnable_filters=True)
+
+
+O_ENC = "modality_encoders.AUDIO."
