@@ -1134,30 +1134,15 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         a2v_set_error("attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return A2V_ERR_CUDA;
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaSuccess;
-#define A2V_ATT_CFG(P_, D_)                                                                                   \
-    if (e == cudaSuccess)                                                                                     \
-        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_, false>,                                      \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL);                \
-    if (e == cudaSuccess)                                                                                     \
-        e = cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<P_, D_, true>,                                       \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM_TOTAL);
-        A2V_ATT_CFG(false, false) A2V_ATT_CFG(false, true) A2V_ATT_CFG(true, false) A2V_ATT_CFG(true, true)
-#undef A2V_ATT_CFG
-        if (e != cudaSuccess) {
-            a2v_set_error("attention: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
     const bool has_pos = p.pos != nullptr, drop = p.drop_p > 0.f;
     const bool trim = p.L <= 512;
-#define A2V_ATT_GO(P_, D_)                                                                       \
-    do {                                                                                         \
-        if (trim) attn_fwd_tcgen05_kernel<P_, D_, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);  \
-        else attn_fwd_tcgen05_kernel<P_, D_, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);      \
+#define A2V_ATT_GO(P_, D_)                                                                                         \
+    do {                                                                                                           \
+        const void* kf = trim ? reinterpret_cast<const void*>(attn_fwd_tcgen05_kernel<P_, D_, true>)               \
+                              : reinterpret_cast<const void*>(attn_fwd_tcgen05_kernel<P_, D_, false>);             \
+        if (a2v_ensure_dynamic_smem(kf, ATT_SMEM_TOTAL) != A2V_OK) return A2V_ERR_CUDA;                            \
+        if (trim) attn_fwd_tcgen05_kernel<P_, D_, true><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);                 \
+        else attn_fwd_tcgen05_kernel<P_, D_, false><<<grid, 128, ATT_SMEM_TOTAL, st>>>(tm, p);                     \
     } while (0)
     if (has_pos && drop) A2V_ATT_GO(true, true);
     else if (has_pos) A2V_ATT_GO(true, false);
@@ -1199,15 +1184,10 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         A2V_REQUIRE(p.H <= a2v_num_sms(), "attention backward: fused qkv-bias gradient needs H <= number of SMs");
         p.dbias = d->dqkv_colsum;
     }
-    static EncodeTiledFn2 encode = nullptr;
+    EncodeTiledFn2 encode = attn_tensor_map_encoder();
     if (encode == nullptr) {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess || !sym) {
-            a2v_set_error("attention: cuTensorMapEncodeTiled not available");
-            return A2V_ERR_CUDA;
-        }
-        encode = reinterpret_cast<EncodeTiledFn2>(sym);
+        a2v_set_error("attention: cuTensorMapEncodeTiled not available");
+        return A2V_ERR_CUDA;
     }
     A2V_REQUIRE((reinterpret_cast<uintptr_t>(p.qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.dout) & 15) == 0,
                 "attention backward: qkv / dout not 16-byte aligned");
@@ -1230,19 +1210,10 @@ extern "C" int a2v_attn_bwd(const a2v_attn_desc* d, a2v_stream_t stream) {
             return A2V_ERR_CUDA;
         }
     }
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             BT_SMEM_TOTAL);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     BT_SMEM_TOTAL);
-        if (e != cudaSuccess) {
-            a2v_set_error("attention backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
+    if (a2v_ensure_dynamic_smem(p.drop_p > 0.f ? reinterpret_cast<const void*>(attn_bwd_tcgen05_kernel<true>)
+                                               : reinterpret_cast<const void*>(attn_bwd_tcgen05_kernel<false>),
+                                BT_SMEM_TOTAL) != A2V_OK)
+        return A2V_ERR_CUDA;
     const int heads = p.batch * p.H;
     const int grid = heads < a2v_num_sms() ? heads : a2v_num_sms();
     if (p.drop_p > 0.f)

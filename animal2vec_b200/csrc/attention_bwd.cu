@@ -461,14 +461,10 @@ int attn_bwd_tiled_launch(const AttnParams& p, cudaStream_t st) {
     if (rc != A2V_OK) return rc;
     rc = attn_make_map(&tg, p.dout, p.D, p.L, p.batch, 128);
     if (rc != A2V_OK) return rc;
-    // per-device attribute: set on every launch (a few hundred ns) instead of a process-wide flag
-    cudaError_t e = p.drop_p > 0.f
-        ? cudaFuncSetAttribute(attn_bwd_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_TOTAL)
-        : cudaFuncSetAttribute(attn_bwd_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GB_SMEM_TOTAL);
-    if (e != cudaSuccess) {
-        a2v_set_error("attention backward: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    if (a2v_ensure_dynamic_smem(p.drop_p > 0.f ? reinterpret_cast<const void*>(attn_bwd_tiled_kernel<true>)
+                                               : reinterpret_cast<const void*>(attn_bwd_tiled_kernel<false>),
+                                GB_SMEM_TOTAL) != A2V_OK)
         return A2V_ERR_CUDA;
-    }
     const int n_t = (p.L + 127) / 128;
     const long long items = (long long)p.batch * p.H * n_t;
     const int grid = items < a2v_num_sms() ? (int)items : a2v_num_sms();

@@ -364,12 +364,8 @@ int attn_fwd_short_launch(const AttnParams& p, cudaStream_t st) {
     const int grid = items < cap ? (int)items : cap;
 #define A2V_SH_GO(P_, D_)                                                                                              \
     do {                                                                                                               \
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_short_kernel<P_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             SH_SMEM_TOTAL);                                                           \
-        if (e != cudaSuccess) {                                                                                        \
-            a2v_set_error("attention forward (short): cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));        \
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(attn_fwd_short_kernel<P_, D_>), SH_SMEM_TOTAL) != A2V_OK) \
             return A2V_ERR_CUDA;                                                                                       \
-        }                                                                                                              \
         attn_fwd_short_kernel<P_, D_><<<grid, SH_THREADS, SH_SMEM_TOTAL, st>>>(t128, t32, p);                          \
     } while (0)
     if (has_pos && drop) A2V_SH_GO(true, true);

@@ -2,6 +2,9 @@
 // device queries.
 #include <stdarg.h>
 #include <stdio.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
 
@@ -20,6 +23,29 @@ int a2v_check_launch(const char* what) {
         a2v_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
         return A2V_ERR_CUDA;
     }
+    return A2V_OK;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function setting: the opt-in is recorded per
+// (function, device) under a mutex, so a process that drives several GPUs (or launches from several threads) configures
+// every kernel on every device exactly once and never skips a device because another one was configured first.
+int a2v_ensure_dynamic_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        a2v_set_error("cudaGetDevice failed");
+        return A2V_ERR_CUDA;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[std::make_pair(func, dev)];
+    if (bytes <= have) return A2V_OK;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        a2v_set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %zu) failed: %s", bytes, cudaGetErrorString(e));
+        return A2V_ERR_CUDA;
+    }
+    have = bytes;
     return A2V_OK;
 }
 

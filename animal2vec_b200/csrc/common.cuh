@@ -14,6 +14,8 @@
 
 void a2v_set_error(const char* fmt, ...);
 int a2v_check_launch(const char* what);
+// opt a kernel into `bytes` of dynamic shared memory on the CURRENT device (once per function and device, thread safe)
+int a2v_ensure_dynamic_smem(const void* func, size_t bytes);
 
 #define A2V_REQUIRE(cond, ...)                         \
     do {                                               \

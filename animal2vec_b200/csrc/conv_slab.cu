@@ -532,15 +532,7 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     if ((rc = cs_make_map(&tw, d->w, d->ldw, (long long)d->groups * d->w_group_rows, 1, d->ldw, 64, "w")) != A2V_OK)
         return rc;
     const int smem = 2 * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_EPI_BYTES + 1024;
-    static int configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_slab_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) {
-            a2v_set_error("conv_slab: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
-            return A2V_ERR_CUDA;
-        }
-        configured = smem;
-    }
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_fwd_kernel), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
     const int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
     conv_slab_fwd_kernel<<<grid, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
     return a2v_check_launch("conv_slab_fwd");
@@ -590,15 +582,7 @@ extern "C" int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t l
     if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, CW_SLAB_ROWS, "x")) != A2V_OK) return rc;
     if ((rc = cs_make_map(&tdy, d->w, d->ldw, d->T, d->batch, d->ldw, 64, "dy")) != A2V_OK) return rc;
     const int smem = CW_STAGES * CW_STAGE_BYTES + 256 + CS_EPI_BYTES + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_slab_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) {
-            a2v_set_error("conv_slab_wgrad: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_wgrad_kernel), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
     conv_slab_wgrad_kernel<<<p.num_tiles, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tdy, p);
     return a2v_check_launch("conv_slab_wgrad");
 }

@@ -263,21 +263,16 @@ extern "C" int a2v_layer_mean_head_fwd(int dtype, const void* const* layers, int
     A2V_REQUIRE(smem <= 200 * 1024, "layer_mean_head_fwd: head weight (%zu bytes) does not fit shared memory", smem);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = flat_blocks(rows, 8);
-    cudaError_t e;
     if (dtype == A2V_F32) {
-        e = cudaFuncSetAttribute(layer_mean_head_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            layer_mean_head_fwd_kernel<float><<<grid, 256, smem, st>>>(reinterpret_cast<const float* const*>(layers), K, rows,
-                                                                        D, C, W, bias, reinterpret_cast<float*>(xmean), logits);
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(layer_mean_head_fwd_kernel<float>), smem) != A2V_OK)
+            return A2V_ERR_CUDA;
+        layer_mean_head_fwd_kernel<float><<<grid, 256, smem, st>>>(reinterpret_cast<const float* const*>(layers), K, rows, D, C,
+                                                                    W, bias, reinterpret_cast<float*>(xmean), logits);
     } else {
-        e = cudaFuncSetAttribute(layer_mean_head_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            layer_mean_head_fwd_kernel<bf16><<<grid, 256, smem, st>>>(reinterpret_cast<const bf16* const*>(layers), K, rows,
-                                                                       D, C, W, bias, reinterpret_cast<bf16*>(xmean), logits);
-    }
-    if (e != cudaSuccess) {
-        a2v_set_error("layer_mean_head_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-        return A2V_ERR_CUDA;
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(layer_mean_head_fwd_kernel<bf16>), smem) != A2V_OK)
+            return A2V_ERR_CUDA;
+        layer_mean_head_fwd_kernel<bf16><<<grid, 256, smem, st>>>(reinterpret_cast<const bf16* const*>(layers), K, rows, D, C, W,
+                                                                   bias, reinterpret_cast<bf16*>(xmean), logits);
     }
     return a2v_check_launch("layer_mean_head_fwd");
 }

@@ -504,14 +504,7 @@ static int g2_make_map(CUtensorMap* m, const a2v_operand& o, int box_rows = 128)
 template <int EPI>
 static int g2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, cudaStream_t st) {
     auto kern = gemm2cta_kernel<EPI>;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) {
-            a2v_set_error("gemm(2cta): cudaFuncSetAttribute failed");
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (size_t)G2_SMEM) != A2V_OK) return A2V_ERR_CUDA;
     int pairs = a2v_num_sms() / 2;
     if (pairs > p.num_tiles) pairs = p.num_tiles;
     cudaLaunchConfig_t cfg;
@@ -568,14 +561,7 @@ static int g2_try_tn(const a2v_gemm_desc* d, cudaStream_t st) {
     CUtensorMap ta, tb;
     if (g2_make_map(&ta, d->a, 64) != 0 || g2_make_map(&tb, d->b, 64) != 0) return -1;
     auto kern = gemm2cta_tn_kernel;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM) != cudaSuccess) {
-            a2v_set_error("gemm(2cta, tn): cudaFuncSetAttribute failed");
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (size_t)G2_SMEM) != A2V_OK) return A2V_ERR_CUDA;
     int pairs = pairs_total < p.num_tiles ? pairs_total : p.num_tiles;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

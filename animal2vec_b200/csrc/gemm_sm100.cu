@@ -677,16 +677,8 @@ static int make_map(CUtensorMap* m, const a2v_operand& o, int box_rows, const ch
 template <int BLOCK_N, int MODE, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
     using S = GemmSmem<BLOCK_N, epi_is_wide<EPI>()>;
-    static bool configured = false;
     auto kern = gemm_tcgen05_kernel<BLOCK_N, MODE, EPI>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-        if (e != cudaSuccess) {
-            a2v_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-            return A2V_ERR_CUDA;
-        }
-        configured = true;
-    }
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (size_t)S::TOTAL) != A2V_OK) return A2V_ERR_CUDA;
     int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
     kern<<<grid, epi_is_wide<EPI>() ? GEMM_THREADS_WIDE : GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
     return a2v_check_launch("gemm_tcgen05_kernel");

@@ -99,11 +99,8 @@ extern "C" int a2v_mixup_gain(const float* x, const float* hann, const float* aw
     A2V_REQUIRE(B > 0 && n_fft >= 2 && n_fft <= 8192 && hop > 0 && N >= n_fft, "mixup_gain: bad extents");
     const int W = (N - n_fft) / hop + 1;
     const size_t smem = (size_t)3 * n_fft * sizeof(float);
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        cudaFuncSetAttribute(mixup_gain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
+    if (smem > 48 * 1024 && a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(mixup_gain_kernel), smem) != A2V_OK)
+        return A2V_ERR_CUDA;
     dim3 grid(W, B);
     mixup_gain_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         x, hann, aweight, N, n_fft, hop, W, powf(10.0f, min_db / 10.0f), gain_db);

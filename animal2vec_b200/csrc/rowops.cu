@@ -1115,16 +1115,9 @@ static int launch_resln_fast(const RowLnParams& p, bool bwd, float* dbias_b, cud
     if (grid < 1) grid = 1;
 #define A2V_RES(KF, KB)                                                                                          \
     do {                                                                                                         \
-        static size_t conf[2] = {0, 0};                                                                          \
-        if (smem > conf[bwd ? 1 : 0]) {                                                                          \
-            cudaError_t e = bwd ? cudaFuncSetAttribute(KB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) \
-                                : cudaFuncSetAttribute(KF, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) {                                                                              \
-                a2v_set_error("rowln(res): cudaFuncSetAttribute(%zu) failed", smem);                             \
-                return A2V_ERR_CUDA;                                                                             \
-            }                                                                                                    \
-            conf[bwd ? 1 : 0] = smem;                                                                            \
-        }                                                                                                        \
+        if (a2v_ensure_dynamic_smem(bwd ? reinterpret_cast<const void*>(KB) : reinterpret_cast<const void*>(KF), smem) !=  \
+            A2V_OK)                                                                                              \
+            return A2V_ERR_CUDA;                                                                                 \
         if (bwd) KB<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages, dbias_b);                                    \
         else KF<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages);                                                 \
     } while (0)
@@ -1168,14 +1161,7 @@ static int launch_rowln_fast(const RowLnParams& p, bool bwd, cudaStream_t st) {
 #define A2V_FAST(KERNEL)                                                                                         \
     do {                                                                                                         \
         auto k = KERNEL;                                                                                         \
-        static size_t conf = 0;                                                                                  \
-        if (smem > conf) {                                                                                       \
-            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
-                a2v_set_error("rowln(fast): cudaFuncSetAttribute(%zu) failed", smem);                            \
-                return A2V_ERR_CUDA;                                                                             \
-            }                                                                                                    \
-            conf = smem;                                                                                         \
-        }                                                                                                        \
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem) != A2V_OK) return A2V_ERR_CUDA;      \
         k<<<grid, ROWLN_WARPS * 32, smem, st>>>(p, stages, cm);                                                   \
     } while (0)
 #define A2V_FAST_NV(N)                                                          \
@@ -1222,17 +1208,9 @@ static int launch_rowln(const RowLnParams& p, bool bwd, cudaStream_t st) {
     do {                                                                                                  \
         auto kf = rowln_fwd_kernel<T, N, F, A, AF>;                                                       \
         auto kb = rowln_bwd_kernel<T, N, F, A, AF>;                                                       \
-        static size_t conf_arr[2] = {0, 0};                                                               \
-        size_t& conf = conf_arr[bwd ? 1 : 0];                                                             \
-        if (smem > conf) {                                                                                \
-            cudaError_t e = bwd ? cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) \
-                                : cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) {                                                                       \
-                a2v_set_error("rowln: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e)); \
-                return A2V_ERR_CUDA;                                                                      \
-            }                                                                                             \
-            conf = smem;                                                                                  \
-        }                                                                                                 \
+        if (a2v_ensure_dynamic_smem(bwd ? reinterpret_cast<const void*>(kb) : reinterpret_cast<const void*>(kf), smem) != \
+            A2V_OK)                                                                                       \
+            return A2V_ERR_CUDA;                                                                          \
         if (bwd)                                                                                          \
             kb<<<grid, threads, smem, st>>>(p, stages);                                                   \
         else                                                                                              \
