@@ -28,8 +28,13 @@ constexpr int ATT_SMEM_Q = 0;
 constexpr int ATT_SMEM_K = 16384;             // 2 buffers
 constexpr int ATT_SMEM_V = 16384 * 3;         // 2 buffers
 constexpr int ATT_SMEM_POS = 16384 * 5;       // 128 floats (key positions of the current tile)
-constexpr int ATT_SMEM_BAR = ATT_SMEM_POS + 512;
-// 80.6 KB (the probabilities live in tensor memory, not in shared memory): two CTAs per SM. The dynamic window
+// ALiBi inside the score product (contiguous sequences): three 128 x 16 bf16 operands without swizzle (8 x 8 core
+// matrices of 128 B; K-adjacent ones 128 B apart, 8-row groups 256 B apart) -- the key-column index, and +/- the slope
+// split into three bf16 pieces
+constexpr int ATT_SMEM_EXT = ATT_SMEM_POS + 512;
+constexpr int ATT_EXT_BYTES = 4096;
+constexpr int ATT_SMEM_BAR = ATT_SMEM_EXT + 3 * ATT_EXT_BYTES;
+// 92.6 KB (the probabilities live in tensor memory, not in shared memory): two CTAs per SM. The dynamic window
 // of a kernel without static shared memory starts 1024-aligned (checked at run time, trap otherwise).
 constexpr int ATT_SMEM_TOTAL = ATT_SMEM_BAR + 128;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units: the running maximum may lag by up to 2^8
@@ -41,10 +46,18 @@ constexpr float ATT_SKIP_LOG2 = 50.0f;
 
 // Flash-style forward. One thread per query row; per 128-key tile:
 //   S = Q K^T (tcgen05, TMEM)  ->  ONE TMEM read into registers, ALiBi + running max in log2 units
-//   ->  P = exp2(S - m) as bf16 into swizzled smem  ->  O += P V accumulated IN TMEM (tcgen05).
+//   ->  P = exp2(S - m) as packed bf16 into TMEM  ->  O += P V accumulated IN TMEM (tcgen05, A operand from TMEM).
 // O is rescaled in TMEM only when a row's maximum grows by more than 2^8 (lazy rescaling), the S MMA of
 // the next tile is issued before the softmax of this one finishes, K and V tiles have separate
 // barriers so the next K can land while V is still being consumed.
+// Contiguous sequences (ncu, profiles/r2_ncu_attn_teacher.md: the kernel is co-limited by issue slots and the MUFU
+// queue, ~50 % each, 895 warp instructions per 128 x 128 tile):
+//  * the key tiles are visited diagonal first, then outwards: the running maximum is (nearly) final after the first
+//    tile, so the O accumulator is not rescaled on the way towards the diagonal;
+//  * off the diagonal |i - j| is linear in the key column, and that term rides in the score product as a fifth K step
+//    (A = the slope in three bf16 pieces, B = the column index; exact products, fp32 accumulation) -- no per-element
+//    FFMA for the bias;
+//  * the exponent arguments and the row sums use packed fp32 pairs (FFMA2 / FADD2).
 #ifdef A2V_ATTN_TRACE
 __device__ long long g_ft_trace[64];
 #define FT_TR(k) do { if (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 1 && j == 6 && tid == 0) g_ft_trace[k] = clock64(); } while (0)
@@ -58,6 +71,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0u) __trap();  // the 128B-swizzled tiles need 1024-byte alignment
+    // second launch after attention_stream.cu: only the heads that kernel declined
+    if (!HAS_POS && p.head_filter == 1 && attn_stream_head_ok(p, blockIdx.z, blockIdx.y)) return;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATT_SMEM_BAR);
     uint64_t* bar_q = bars;
     uint64_t* bar_k = bars + 1;  // [2]
@@ -99,6 +114,24 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         mbar_fence_init();
         fence_proxy_async();
     }
+    const float kappa = head_coef(p, h) / p.sm_scale;  // ALiBi slope in units of the raw q.k product
+    const bool use_ext = !HAS_POS && kappa != 0.f;
+    if (use_ext) {
+        const __nv_bfloat16 k1 = __float2bfloat16_rn(kappa);
+        const __nv_bfloat16 k2 = __float2bfloat16_rn(kappa - __bfloat162float(k1));
+        const __nv_bfloat16 k3 = __float2bfloat16_rn(kappa - __bfloat162float(k1) - __bfloat162float(k2));
+        const uint32_t b1 = __bfloat16_as_ushort(k1), b2 = __bfloat16_as_ushort(k2), b3 = __bfloat16_as_ushort(k3);
+        const uint32_t bc = __bfloat16_as_ushort(__float2bfloat16_rn((float)tid));  // 0..127: exact
+        uint8_t* ext = smem + ATT_SMEM_EXT + (tid >> 3) * 256 + (tid & 7) * 16;      // row tid, K elements 0..7
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(ext) = make_uint4(bc | (bc << 16), bc, 0u, 0u);                                  // key column
+        *reinterpret_cast<uint4*>(ext + ATT_EXT_BYTES) = make_uint4(b1 | (b2 << 16), b3, 0u, 0u);                  // + slope
+        *reinterpret_cast<uint4*>(ext + 2 * ATT_EXT_BYTES) = make_uint4((b1 | (b2 << 16)) ^ 0x80008000u, b3 ^ 0x8000u, 0u, 0u);  // - slope
+        *reinterpret_cast<uint4*>(ext + 128) = zero;                                                               // K elements 8..15
+        *reinterpret_cast<uint4*>(ext + ATT_EXT_BYTES + 128) = zero;
+        *reinterpret_cast<uint4*>(ext + 2 * ATT_EXT_BYTES + 128) = zero;
+        fence_proxy_async();
+    }
     if (warp == 0) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
     __syncthreads();
@@ -112,12 +145,27 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
     const uint32_t qa = smem_u32(smem + ATT_SMEM_Q);
 
-    auto issue_s = [&](int buf) {
+    // key tile of iteration jj: ascending for token positions; contiguous sequences start on the diagonal tile
+    // (= this CTA's query tile) and walk outwards, left side first
+    const int diag = blockIdx.x;
+    auto tile_of = [&](int jj) -> int {
+        if (HAS_POS) return j_begin + jj;
+        const int nl = diag - j_begin;
+        return jj == 0 ? diag : (jj <= nl ? diag - jj : j_begin + jj);
+    };
+    // tiles whose ALiBi term is linear in the key column: everything but the diagonal and the ragged last tile
+    auto is_linear = [&](int j) -> bool { return !HAS_POS && j != n_kv - 1 && j != diag; };
+    auto issue_s = [&](int buf, int j) {
         const uint32_t ka = smem_u32(smem + ATT_SMEM_K + buf * 16384);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
             umma_bf16(tmem_s, umma_smem_desc(qa + k * 32, 0, 1024), umma_smem_desc(ka + k * 32, 0, 1024), idesc_s,
                       k > 0 ? 1u : 0u);
+        if (use_ext && is_linear(j)) {  // + sg * slope * column: keys before the query rows count up, keys after count down
+            const uint32_t ea = smem_u32(smem + ATT_SMEM_EXT);
+            umma_bf16(tmem_s, umma_smem_desc_nosw(ea + (j < diag ? 1 : 2) * ATT_EXT_BYTES, 128, 256),
+                      umma_smem_desc_nosw(ea, 128, 256), idesc_s, 1u);
+        }
         umma_commit(bar_s);
     };
 
@@ -125,17 +173,17 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         mbar_expect_tx(bar_q, 16384);
         tma_load_3d(smem + ATT_SMEM_Q, &tm, bar_q, h * HD, q0, b);
         mbar_expect_tx(&bar_k[0], 16384);
-        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_k[0], D + h * HD, j_begin * 128, b);
+        tma_load_3d(smem + ATT_SMEM_K, &tm, &bar_k[0], D + h * HD, tile_of(0) * 128, b);
         mbar_expect_tx(&bar_v[0], 16384);
-        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_v[0], 2 * D + h * HD, j_begin * 128, b);
+        tma_load_3d(smem + ATT_SMEM_V, &tm, &bar_v[0], 2 * D + h * HD, tile_of(0) * 128, b);
         if (n_it > 1) {
             mbar_expect_tx(&bar_k[1], 16384);
-            tma_load_3d(smem + ATT_SMEM_K + 16384, &tm, &bar_k[1], D + h * HD, j_begin * 128 + 128, b);
+            tma_load_3d(smem + ATT_SMEM_K + 16384, &tm, &bar_k[1], D + h * HD, tile_of(1) * 128, b);
         }
         mbar_wait(bar_q, 0);
         mbar_wait(&bar_k[0], 0);
         tc_fence_after();
-        issue_s(0);
+        issue_s(0, tile_of(0));
     }
 
     const int qi = q0 + tid;  // this thread's query row
@@ -143,7 +191,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const int pos_i = q_ok ? (HAS_POS ? p.pos[(long long)b * L + qi] : qi) : 0;
     const float coef2 = head_coef(p, h) * LOG2E;
     const float scale2 = p.sm_scale * LOG2E;
-    const float kappa = coef2 / scale2;
     const float inv_keep = DROP ? 1.0f / (1.0f - p.drop_p) : 1.0f;
     const long long bh = (long long)b * p.H + h;
     const uint32_t row_key = DROP ? attn_row_key(p.seed, bh, L, qi) : 0u;
@@ -154,7 +201,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const bool warp_active = !TRIM || (q0 + warp * 32) < L;  // TRIM: short sequences (student), skip dead work
 
     for (int jj = 0; jj < n_it; ++jj) {  // jj: iteration (buffers, barrier phases); j: key tile (positions)
-        const int j = j_begin + jj;
+        const int j = tile_of(jj);
         const int buf = jj & 1;
         const int k0 = j * 128;
         const bool last = (j == n_kv - 1);
@@ -170,23 +217,23 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         FT_TR(1);
         if (warp == 0 && elect_one() && jj + 2 < n_it) {  // K buffer `buf` is free: S(j) has been computed
             mbar_expect_tx(&bar_k[buf], 16384);
-            tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, k0 + 256, b);
+            tma_load_3d(smem + ATT_SMEM_K + buf * 16384, &tm, &bar_k[buf], D + h * HD, tile_of(jj + 2) * 128, b);
         }
 
         // scores -> registers, row maximum. t[] holds u with  score(log2 units) = u * e_mul + c_row:
         //  * generic tiles (token positions, the diagonal tile, the ragged last tile): u = score, e_mul = 1, c_row = 0;
         //  * every other tile of a contiguous sequence lies entirely before or after this CTA's query rows, so
-        //    |i - j| is linear in the key column: score = scale2 * (raw + sg*kappa*col) + c_row with a per-row
-        //    constant c_row -- two FFMAs and half an FMNMX per element, the constant folds into the exp2 offset.
+        //    |i - j| is linear in the key column and already inside the product: score = scale2 * raw' + c_row with a
+        //    per-row constant c_row that folds into the exp2 offset -- half an FMNMX3 per element in this pass.
         float t[128];
         float m_tile = -INFINITY;
         float e_mul = 1.0f, c_row = 0.f;
         const float dist0 = (float)(pos_i - k0);
         const float fpos_i = (float)pos_i;
         const int nvalid = L - k0;  // keys of this tile that exist (>= 128 except for the last tile)
-        if (!HAS_POS && !last && j != (int)blockIdx.x) {
-            const float sg = j < (int)blockIdx.x ? 1.0f : -1.0f;
-            const float kap = sg * kappa;
+        if (is_linear(j)) {
+            // the product already holds raw + sg * slope * column (fifth K step of issue_s)
+            const float sg = j < diag ? 1.0f : -1.0f;
             float m_u = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -195,7 +242,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float u = fmaf(kap, (float)(c * 32 + i), __uint_as_float(raw[i]));
+                    const float u = __uint_as_float(raw[i]);
                     t[c * 32 + i] = u;
                     m_u = fmaxf(m_u, u);
                 }
@@ -239,7 +286,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 mbar_wait(&bar_k[buf ^ 1], ((jj + 1) >> 1) & 1);
                 tc_fence_after();
                 FT_TR(8);
-                issue_s(buf ^ 1);
+                issue_s(buf ^ 1, tile_of(jj + 1));
                 FT_TR(9);
 #ifdef A2V_ATTN_TRACE
                 if (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 1 && j == 6) {
@@ -257,7 +304,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         FT_TR(3);
         if (warp == 0 && elect_one() && jj + 1 < n_it) {
             mbar_expect_tx(&bar_v[buf ^ 1], 16384);
-            tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, k0 + 128, b);
+            tma_load_3d(smem + ATT_SMEM_V + (buf ^ 1) * 16384, &tm, &bar_v[buf ^ 1], 2 * D + h * HD, tile_of(jj + 1) * 128, b);
         }
         // lazy rescaling of O (in TMEM) and of the running sum
         const bool grow = m_tile > m_run + ATT_RESCALE_THRESHOLD;  // also true on the first tile (m_run = -inf)
@@ -280,7 +327,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         // probabilities -> TENSOR memory (packed bf16 pairs, 16 columns per 32 keys): the A operand of P.V is read
         // from TMEM, so P costs no shared-memory bandwidth (S and P.V operands out of smem were the bottleneck:
         // 144 KB per 128x128 tile against 128 B/clk)
-        float l_tile = 0.f;
+        float2 l2 = make_float2(0.f, 0.f);
         const float e_off = c_row - m_run;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -294,9 +341,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
                 for (int u = 0; u < 4; ++u) {
                     float e[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        e[i] = ex2_approx(fmaf(t[c * 32 + u * 8 + i], e_mul, e_off));
-                        l_tile += e[i];
+                    for (int i = 0; i < 8; i += 2) {  // packed fp32 pairs: one FFMA2 / FADD2 per two keys
+                        const float2 a = __ffma2_rn(make_float2(t[c * 32 + u * 8 + i], t[c * 32 + u * 8 + i + 1]),
+                                                    make_float2(e_mul, e_mul), make_float2(e_off, e_off));
+                        e[i] = ex2_approx(a.x);
+                        e[i + 1] = ex2_approx(a.y);
+                        l2 = __fadd2_rn(l2, make_float2(e[i], e[i + 1]));
                     }
                     if (DROP) {
 #pragma unroll
@@ -316,6 +366,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
             }
             tmem_st_32x16(tmem_p + lane_off + c * 16, pk);
         }
+        const float l_tile = l2.x + l2.y;
         tmem_st_wait();
         l_run += l_tile;
         FT_TR(4);
@@ -1075,6 +1126,7 @@ int validate_attn(const a2v_attn_desc* d, AttnParams& p) {
     p.delta = nullptr;
     p.dq_acc = nullptr;
     p.dbias = nullptr;
+    p.head_filter = 0;
     return A2V_OK;
 }
 
@@ -1116,6 +1168,18 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         use_short = (e == nullptr || e[0] != '0') ? 1 : 0;
     }
     if (use_short == 1 && p.L <= ATTN_SHORT_LMAX) return attn_fwd_short_launch(p, st);
+    // contiguous sequences with the q/k bound: single-pass stream kernel first, the flash kernel below then only runs the
+    // heads whose norms are too large for a fixed reference exponent (A2V_ATTN_STREAM=0: flash kernel for everything)
+    static int use_stream = -1;
+    if (use_stream < 0) {
+        const char* e = getenv("A2V_ATTN_STREAM");
+        use_stream = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    if (use_stream == 1 && p.pos == nullptr && p.qk_bound != nullptr && p.L > ATTN_SHORT_LMAX) {
+        rc = attn_fwd_stream_launch(p, st);
+        if (rc != A2V_OK) return rc;
+        p.head_filter = 1;
+    }
     EncodeTiledFn2 encode = attn_tensor_map_encoder();
     if (encode == nullptr) {
         a2v_set_error("attention: cuTensorMapEncodeTiled not available");

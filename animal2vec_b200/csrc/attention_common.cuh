@@ -31,6 +31,7 @@ struct AttnParams {
     const float* delta;     // (batch, H, L) rowsum(dO * O)
     float* dq_acc;          // (batch, L, D) fp32 accumulator of dQ (unscaled)
     float* dbias;           // optional (resident backward): += column sums of dqkv, (3 * D) fp32 = the qkv bias gradient
+    int head_filter;        // flash forward: 1 = only the heads attention_stream.cu declined (attn_stream_head_ok false)
 };
 
 // Column sums over the 32 lanes of a warp for N columns held per lane (N = 16 or 32): a transposing butterfly, N - 1
@@ -83,6 +84,13 @@ __device__ __forceinline__ bool attn_keep(unsigned long long seed, long long bh,
     return ((w >> (16 * (j & 1))) & 0xffffu) >= attn_drop_threshold(pd);
 }
 
+// attention_stream.cu exponentiates against a fixed per-row reference, which needs 2 max|q| max|k| scale <= 96 log2
+// units; the same test (same arithmetic) lets the flash kernel pick up exactly the heads the stream kernel declined
+__device__ __forceinline__ bool attn_stream_head_ok(const AttnParams& p, int b, int h) {
+    const float2 b2 = reinterpret_cast<const float2*>(p.qk_bound)[b * p.H + h];  // max|q|^2, max|k|^2
+    return 2.f * (sqrtf(b2.x) * sqrtf(b2.y) * 1.002f) * (p.sm_scale * LOG2E) <= 96.f;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -131,5 +139,8 @@ int attn_bwd_tiled_launch(const AttnParams& p, cudaStream_t st);
 // attention_short.cu: persistent single-pass forward for the student's short sequences (L <= 160)
 int attn_fwd_short_launch(const AttnParams& p, cudaStream_t st);
 constexpr int ATTN_SHORT_LMAX = 160;
+// attention_stream.cu: single-pass forward for contiguous sequences with the q/k bound (p.qk_bound); heads it declines
+// are left untouched for the flash kernel launched with head_filter = 1
+int attn_fwd_stream_launch(const AttnParams& p, cudaStream_t st);
 
 }  // namespace a2v

@@ -349,6 +349,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
+// UMMA shared-memory descriptor WITHOUT swizzle (layout_type 0), K-major: 8 x 8-element core matrices of 128 contiguous
+// bytes (8 rows of 16 B); the core matrix next in K is lbo_bytes away, the next 8-row group sbo_bytes away.
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;
+}
 // instruction descriptor for kind::f16 with bf16 A/B and fp32 D
 __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n, bool a_mn_major, bool b_mn_major) {
     uint32_t d = 0;

@@ -340,7 +340,7 @@ def run_b200(args):
                                "Linear shapes (QKV, proj, fc1, fc2, decoder / feature projections, strided-conv GEMMs; forward, "
                                "data and weight gradients): every launch with taps = groups = batch = 1",
                      "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic_per_launch("gemm2cta"),
+                     "frac": achieved / peaks["tflops_sustained"], "traffic": traffic_per_launch("gemm2cta_kernel"),
                      "flops": "algorithmic = executed for these shapes (2 M N K, no padding)",
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      "launches": gemm_n, "share_of_step": gemm_ms / ms_total,

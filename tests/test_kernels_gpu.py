@@ -286,14 +286,47 @@ def test_attention_alibi_locality_skip_is_exact(qk_scale, seq):
     scale[5] = 0.0
     full, lse_full = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale)
     fast, lse_fast = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale, skip_far_keys=True)
-    # P is rounded to bf16 relative to a lazily updated running maximum, which evolves differently when the sweep
-    # starts next to the diagonal: the two results differ by that (decorrelated) rounding noise only -- both sit at the
-    # same distance from fp32 torch math, and the fp32 log-sum-exp agrees to rounding
-    assert _rel(fast, full) < 1e-3, _rel(fast, full)
+    # P is rounded to bf16 relative to a different reference exponent in the two sweeps (a lazily updated running
+    # maximum in the flash kernel, none at all in the single-pass stream kernel that takes the windowed call when the
+    # q/k norms allow it): the two results differ by that decorrelated rounding noise only -- both sit at the same
+    # distance from fp32 torch math, and the fp32 log-sum-exp agrees to rounding
+    assert _rel(fast, full) < 4e-3, _rel(fast, full)
     assert _rel(lse_fast, lse_full) < 1e-5
     ref = _attn_ref(qkv, batch, seq, heads, None, slopes, scale)
     e_fast, e_full = _rel(fast, ref), _rel(full, ref)
-    assert e_fast < 1e-2 and e_fast < 1.05 * e_full + 1e-4, (e_fast, e_full)
+    # the flash kernel rounds P relative to (nearly) the row maximum, so a row's dominant probabilities are 1.0 or close
+    # to it and round exactly; the stream kernel's P carry a plain bf16 rounding error (2.3e-3 at every slope)
+    assert e_fast < 3e-3 and e_fast < 1.3 * e_full + 1e-4, (e_fast, e_full)
+
+
+def test_attention_stream_and_flash_kernels_split_the_heads_by_norm():
+    """Windowed forward on contiguous sequences: the single-pass stream kernel (no running maximum) takes the heads whose
+    max|q| max|k| allows a fixed exponent reference, the flash kernel (second launch, head filter) the others. Heads of
+    both kinds in one call, with dropout, a ragged length, and a zero-slope head; every head against fp32 torch math."""
+    from animal2vec_b200 import ops
+
+    batch, seq, heads = 2, 1111, 8
+    d = heads * 64
+    qkv = torch.randn(batch, seq, 3 * d, device="cuda", generator=_g(1))
+    big = torch.tensor([1.0, 6.0, 1.0, 0.3, 8.0, 1.0, 5.0, 1.0], device="cuda")  # heads 1, 4, 6: 2 B >> 96 log2 units
+    qkv.view(batch, seq, 3, heads, 64)[:, :, :2] *= big.view(1, 1, 1, heads, 1)
+    qkv = qkv.bfloat16()
+    slopes = torch.tensor([2.0 ** (-8.0 * (h + 1) / heads) for h in range(heads)], device="cuda")
+    scale = torch.rand(heads, device="cuda", generator=_g(3)) + 0.5
+    scale[2] = 0.0
+    out, lse = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale, skip_far_keys=True)
+    ref = _attn_ref(qkv, batch, seq, heads, None, slopes, scale)
+    e = ((out.float() - ref).view(batch, seq, heads, 64).pow(2).sum((0, 1, 3)) /
+         ref.view(batch, seq, heads, 64).pow(2).sum((0, 1, 3))).sqrt()
+    assert float(e.max()) < 1e-2, e
+    q, k, _ = qkv.float().view(batch, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    pos = torch.arange(seq, device="cuda").float()
+    s = (q * 64 ** -0.5) @ k.transpose(-1, -2) - (slopes * scale).view(1, heads, 1, 1) * (pos[:, None] - pos[None, :]).abs()
+    assert _rel(lse, torch.logsumexp(s, -1)) < 1e-4
+    # dropout: both kernels regenerate the same keep hashes, so the windowed call equals the full sweep of the flash kernel
+    a, _ = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale, drop_p=0.2, seed=77, skip_far_keys=True)
+    b, _ = ops.attn_fwd(qkv, batch, seq, heads, slopes=slopes, alibi_scale=scale, drop_p=0.2, seed=77)
+    assert _rel(a, b) < 8e-3, _rel(a, b)
 
 
 def test_attention_dropout_statistics():

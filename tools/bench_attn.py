@@ -24,11 +24,15 @@ slopes = torch.tensor([2.0 ** (-0.5 * (h + 1)) for h in range(H)], device="cuda"
 scale = torch.ones(H, device="cuda")
 for name, batch, L, with_pos, drop in [("teacher", B, 2000, False, 0.0), ("student", B * 12, 142, True, 0.1),
                                        ("student148", B * 12, 148, True, 0.1), ("student128", B * 12, 128, True, 0.1)]:
+    if os.environ.get("ONLY") and os.environ["ONLY"] not in name:
+        continue
     qkv = torch.randn(batch, L, 3 * H * 64, device="cuda").bfloat16()
     pos = None
     if with_pos:
         pos = torch.stack([torch.randperm(2000, device="cuda")[:L].sort().values for _ in range(batch)]).int().contiguous()
-    ms = timeit(lambda: ops.attn_fwd(qkv, batch, L, H, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=drop, seed=1))
+    skip = os.environ.get("SKIP_FAR", "0") == "1" and not with_pos
+    ms = timeit(lambda: ops.attn_fwd(qkv, batch, L, H, pos=pos, slopes=slopes, alibi_scale=scale, drop_p=drop, seed=1,
+                                     skip_far_keys=skip))
     fl = 4.0 * L * L * 64 * H * batch
     print(json.dumps({"kernel": "attn_fwd " + name, "ms": ms, "tflops": fl / ms / 1e9}))
     if L <= 160:
