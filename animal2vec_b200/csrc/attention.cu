@@ -83,30 +83,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     float* spos = reinterpret_cast<float*>(smem + ATT_SMEM_POS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+    const int h = blockIdx.y, b = blockIdx.z;
     const int L = p.L, D = p.D;
     const int n_kv = (L + 127) >> 7;
-    // Key-tile range [j_begin, j_end) of this query tile. Contiguous sequences with an ALiBi slope: with
-    // B = max|q| max|k| of the head, every score obeys |q.k| * scale2 <= B * scale2, the row's own key (distance 0)
-    // floors the running maximum at -B * scale2, so a key at distance d has exponent <= 2 B scale2 - coef2 d (log2).
-    // Tiles whose nearest key is at least w = (2 B scale2 + ATT_SKIP_LOG2) / coef2 frames away contribute nothing.
-    int j_begin = 0, j_end = n_kv;
-    if (!HAS_POS && p.qk_bound != nullptr) {
-        const float c2 = head_coef(p, h) * LOG2E;
-        if (c2 > 0.f) {
-            const float2 b2 = reinterpret_cast<const float2*>(p.qk_bound)[b * p.H + h];  // max|q|^2, max|k|^2
-            const float qk = sqrtf(b2.x) * sqrtf(b2.y) * 1.002f;
-            const float w = (2.f * qk * (p.sm_scale * LOG2E) + ATT_SKIP_LOG2) / c2;
-            if (w < 1.0e6f) {
-                const int wi = (int)w + 1;
-                const int lo = q0 - 127 - wi;  // tile j is kept iff 128 j > lo and 128 j < q0 + 127 + wi
-                j_begin = lo < 0 ? 0 : lo / 128 + 1;
-                const int hi = (q0 + 126 + wi) / 128 + 1;
-                j_end = hi < n_kv ? hi : n_kv;
-            }
-        }
-    }
-    const int n_it = j_end - j_begin;
 
     if (tid == 0) {
         tma_prefetch_desc(&tm);
@@ -145,9 +124,36 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
     const uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
     const uint32_t qa = smem_u32(smem + ATT_SMEM_Q);
 
+    // One query tile per CTA (grid.x = number of query tiles); the head-filtered second launch behind attention_stream.cu
+    // uses grid.x = 1 and walks the query tiles of its (rarely taken) heads here, so a declined launch costs
+    // batch x heads empty CTAs instead of batch x heads x tiles.
+    for (int qt = blockIdx.x; qt < n_kv; qt += gridDim.x) {
+    const int q0 = qt * 128;
+    // Key-tile range [j_begin, j_end) of this query tile. Contiguous sequences with an ALiBi slope: with
+    // B = max|q| max|k| of the head, every score obeys |q.k| * scale2 <= B * scale2, the row's own key (distance 0)
+    // floors the running maximum at -B * scale2, so a key at distance d has exponent <= 2 B scale2 - coef2 d (log2).
+    // Tiles whose nearest key is at least w = (2 B scale2 + ATT_SKIP_LOG2) / coef2 frames away contribute nothing.
+    int j_begin = 0, j_end = n_kv;
+    if (!HAS_POS && p.qk_bound != nullptr) {
+        const float c2 = head_coef(p, h) * LOG2E;
+        if (c2 > 0.f) {
+            const float2 b2 = reinterpret_cast<const float2*>(p.qk_bound)[b * p.H + h];  // max|q|^2, max|k|^2
+            const float qk = sqrtf(b2.x) * sqrtf(b2.y) * 1.002f;
+            const float w = (2.f * qk * (p.sm_scale * LOG2E) + ATT_SKIP_LOG2) / c2;
+            if (w < 1.0e6f) {
+                const int wi = (int)w + 1;
+                const int lo = q0 - 127 - wi;  // tile j is kept iff 128 j > lo and 128 j < q0 + 127 + wi
+                j_begin = lo < 0 ? 0 : lo / 128 + 1;
+                const int hi = (q0 + 126 + wi) / 128 + 1;
+                j_end = hi < n_kv ? hi : n_kv;
+            }
+        }
+    }
+    const int n_it = j_end - j_begin;
+
     // key tile of iteration jj: ascending for token positions; contiguous sequences start on the diagonal tile
     // (= this CTA's query tile) and walk outwards, left side first
-    const int diag = blockIdx.x;
+    const int diag = qt;
     auto tile_of = [&](int jj) -> int {
         if (HAS_POS) return j_begin + jj;
         const int nl = diag - j_begin;
@@ -410,6 +416,21 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams
         }
         if (q_ok && p.lse != nullptr) p.lse[bh * L + qi] = (m_run + log2f(l_run)) * LN2;
     }
+    if (qt + (int)gridDim.x < n_kv) {  // next query tile of this head: every barrier is quiescent, start their phases over
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 0; i < 7; ++i) {
+                mbar_inval(&bars[i]);
+                mbar_init(&bars[i], 1);
+            }
+            mbar_fence_init();
+            fence_proxy_async();
+        }
+        __syncthreads();
+        tc_fence_after();
+    }
+    }  // query tiles
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -1179,6 +1200,7 @@ extern "C" int a2v_attn_fwd(const a2v_attn_desc* d, a2v_stream_t stream) {
         rc = attn_fwd_stream_launch(p, st);
         if (rc != A2V_OK) return rc;
         p.head_filter = 1;
+        grid.x = 1;  // one CTA per (head, sequence): exits at once unless the stream kernel declined the head
     }
     EncodeTiledFn2 encode = attn_tensor_map_encoder();
     if (encode == nullptr) {
