@@ -13,9 +13,10 @@
 // kernel is L2-bandwidth bound. Here one TMA box brings rows [m0 - pad, m0 - pad + 256 + taps - 1) of
 // the group's 64 channels into a 128B-swizzled slab; the A operand of tap j is the SAME shared memory
 // shifted down by j rows (descriptor start address + j*128 B; the 128B swizzle is a function of the
-// absolute shared-memory address, so the shifted view stays consistent with what TMA wrote). Two 128-row output tiles share each weight tile. Warp roles as in gemm_sm100.cu:
-// warp 0 TMA producer, warp 1 tcgen05.mma issuer (one thread), warps 2..5 epilogue out of
-// double-buffered TMEM accumulators.
+// absolute shared-memory address, so the shifted view stays consistent with what TMA wrote). Two 128-row output tiles
+// share each weight tile. Warp roles: warp 0 slab producer (4-stage ring: the activations stream from HBM once, the
+// producer runs tiles ahead), warp 6 weight-tile producer (6-stage ring, L2 resident), warp 1 tcgen05.mma issuer (one
+// thread), warps 2..5 epilogue out of double-buffered TMEM accumulators.
 #include <string.h>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
@@ -26,8 +27,11 @@ constexpr int CS_BLOCK_M = 128;
 constexpr int CS_MT = 2;                        // 128-row tiles per slab
 constexpr int CS_SUPER_M = CS_BLOCK_M * CS_MT;  // output rows per tile
 constexpr int CS_NB = 6;                        // weight-tile ring stages (8 KB each)
+constexpr int CS_NS = 4;                        // slab ring stages: a slab comes from HBM (the activations are streamed once),
+                                                // two stages left the tensor pipe waiting on the load of the tile after next
 constexpr int CS_B_BYTES = 64 * 64 * 2;
 constexpr int CS_THREADS = 192;
+constexpr int CS_FWD_THREADS = 224;             // forward: + warp 6, the weight-tile producer
 constexpr int CS_EPI_PITCH = 36;
 constexpr int CS_EPI_BYTES = 4 * 32 * CS_EPI_PITCH * 4;
 
@@ -41,7 +45,6 @@ struct ConvSlabParams {
     int slab_rows;   // multiple of 16, >= CS_SUPER_M + taps - 1
     int m_tiles;     // ceil(T / CS_SUPER_M)
     int num_tiles;
-    int bo_mode;
     int fast_store;  // bf16 output, 8-column groups 16-byte aligned: bf16 staging + 16-byte stores
 };
 
@@ -84,18 +87,19 @@ __device__ __forceinline__ void cs_store_chunk(const ConvSlabParams& p, const fl
     }
 }
 
-__global__ void __launch_bounds__(CS_THREADS, 1)
+template <int KSTEPS>
+__global__ void __launch_bounds__(CS_FWD_THREADS, 1)
 conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                      const ConvSlabParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int slab_bytes = p.slab_rows * 128;
     uint8_t* slab0 = smem;
-    uint8_t* bring = smem + 2 * slab_bytes;
+    uint8_t* bring = smem + CS_NS * slab_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(bring + CS_NB * CS_B_BYTES);
-    uint64_t* slab_full = bars;            // [2]
-    uint64_t* slab_empty = bars + 2;       // [2]
-    uint64_t* b_full = bars + 4;           // [CS_NB]
+    uint64_t* slab_full = bars;                 // [CS_NS]
+    uint64_t* slab_empty = bars + CS_NS;        // [CS_NS]
+    uint64_t* b_full = bars + 2 * CS_NS;        // [CS_NB]
     uint64_t* b_empty = b_full + CS_NB;    // [CS_NB]
     uint64_t* tfull = b_empty + CS_NB;     // [2]
     uint64_t* tempty = tfull + 2;          // [2]
@@ -108,9 +112,11 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmW);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < CS_NS; ++i) {
             mbar_init(&slab_full[i], 1);
             mbar_init(&slab_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
             mbar_init(&tempty[i], 4);
         }
@@ -127,18 +133,24 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // tile -> (m super tile, batch, group): consecutive tiles share the group's weights (L2 friendly)
+    // tile -> (group, m super tile, batch), group fastest: the CTAs running at the same time read (and write) ALL the
+    // 128-byte group slices of the same activation rows, so every 2 KB row is consumed while its DRAM page is open and
+    // its lines merge in L2 (group-major order streamed one 128-byte slice of every row per pass: ~50 % of the HBM
+    // rate on the 7-tap layers). The weights of all groups (taps x 8 KB each) stay L2 resident either way.
     auto decode = [&](int tile, int& ms, int& b, int& g) {
+        g = tile % p.groups;
+        tile /= p.groups;
         ms = tile % p.m_tiles;
-        tile /= p.m_tiles;
-        b = tile % p.batch;
-        g = tile / p.batch;
+        b = tile / p.m_tiles;
     };
 
     if (warp == 0) {
+        // slab producer: runs up to CS_NS tiles ahead of the tensor pipe, independent of the weight ring (one thread
+        // for both kept the next slab behind the last weight tiles of the current one: ~6 taps of prefetch distance
+        // against an HBM round trip)
         if (elect_one()) {
-            int ss = 0, bs = 0;
-            uint32_t sphase = 0, bphase = 0;
+            int ss = 0;
+            uint32_t sphase = 0;
             const int half_rows = p.slab_rows >> 1;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 int ms, b, g;
@@ -149,7 +161,18 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 const int r0 = ms * CS_SUPER_M - p.pad;
                 tma_load_3d(slab, &tmX, &slab_full[ss], g * 64, r0, b);
                 tma_load_3d(slab + half_rows * 128, &tmX, &slab_full[ss], g * 64, r0 + half_rows, b);
-                if (++ss == 2) { ss = 0; sphase ^= 1; }
+                if (++ss == CS_NS) { ss = 0; sphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 6) {
+        // weight-tile producer
+        if (elect_one()) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                int ms, b, g;
+                decode(tile, ms, b, g);
                 for (int j = 0; j < p.taps; ++j) {
                     mbar_wait(&b_empty[bs], bphase ^ 1);
                     mbar_expect_tx(&b_full[bs], CS_B_BYTES);
@@ -174,14 +197,14 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     tc_fence_after();
                     const uint32_t wb = smem_u32(bring + bs * CS_B_BYTES);
                     // measured on B200: the swizzle phase comes from the absolute smem address bits [7:9]; a row-shifted
-                    // start address needs NO base-offset correction (bo_mode 1 is a debugging aid only)
-                    const uint32_t bo = p.bo_mode == 1 ? (uint32_t)(j & 7) : 0u;
+                    // start address needs NO base-offset correction
+                    const uint32_t bo = 0u;
 #pragma unroll
                     for (int mt = 0; mt < CS_MT; ++mt) {
                         const uint32_t a0 = slab + (uint32_t)(mt * CS_BLOCK_M + j) * 128u;
                         const uint32_t td = tmem_base + as * (CS_MT * 64) + mt * 64;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < KSTEPS; ++k)
                             umma_bf16(td, umma_smem_desc_bo(a0 + k * 32, 1024, bo), umma_smem_desc(wb + k * 32, 0, 1024),
                                       idesc, (j > 0 || k > 0) ? 1u : 0u);
                     }
@@ -190,7 +213,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 }
                 umma_commit(&slab_empty[ss]);
                 umma_commit(&tfull[as]);
-                if (++ss == 2) { ss = 0; sphase ^= 1; }
+                if (++ss == CS_NS) { ss = 0; sphase ^= 1; }
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -523,7 +546,9 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     p.slab_rows = (CS_SUPER_M + d->taps - 1 + 15) & ~15;
     p.m_tiles = ceil_div(d->T, CS_SUPER_M);
     p.num_tiles = p.m_tiles * d->batch * d->groups;
-    p.bo_mode = d->reserved;
+    A2V_REQUIRE(d->x_real_cols >= 0 && d->x_real_cols <= 64, "conv_slab: x_real_cols out of range");
+    // K steps of 16 channels per tap: 3 when the last 16 channels of every input group are zero padding, else 4
+    const int ksteps = (d->x_real_cols > 0 && d->x_real_cols <= 48) ? 3 : 4;
     p.fast_store = !p.y_f32 && d->ng % 8 == 0 && d->ldy % 8 == 0 && d->y_group_cols % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(d->y) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0;
     CUtensorMap tx, tw;
@@ -531,10 +556,15 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, p.slab_rows / 2, "x")) != A2V_OK) return rc;
     if ((rc = cs_make_map(&tw, d->w, d->ldw, (long long)d->groups * d->w_group_rows, 1, d->ldw, 64, "w")) != A2V_OK)
         return rc;
-    const int smem = 2 * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_EPI_BYTES + 1024;
-    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_fwd_kernel), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
+    const int smem = CS_NS * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_EPI_BYTES + 1024;
     const int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
-    conv_slab_fwd_kernel<<<grid, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+    if (ksteps == 3) {
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_fwd_kernel<3>), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
+        conv_slab_fwd_kernel<3><<<grid, CS_FWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+    } else {
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_fwd_kernel<4>), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
+        conv_slab_fwd_kernel<4><<<grid, CS_FWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, p);
+    }
     return a2v_check_launch("conv_slab_fwd");
 }
 

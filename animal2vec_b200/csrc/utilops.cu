@@ -204,11 +204,53 @@ __device__ __forceinline__ void relayout_item_transpose(const a2v_relayout_item&
     }
 }
 
+// The same for fp32 -> bf16 without accumulation (the transposed weight copies of every Linear, 300 M elements per
+// update): 64 x 64 tiles, 16-byte loads along K, 4-byte (bf16 pair) stores along N -- four times the bytes in flight per
+// block of the 32 x 32 version, which ran at 1.2 TB/s (ncu, profiles/r2_ncu_summary.md).
+__device__ __forceinline__ void relayout_item_transpose64(const a2v_relayout_item& it, float (*tile)[65]) {
+    const float* in = reinterpret_cast<const float*>(it.in) + it.in_offset;
+    bf16* out = reinterpret_cast<bf16*>(it.out) + it.out_offset;
+    const int K = (int)it.dims[2], N = (int)it.dims[3];
+    const long long is3 = it.in_strides[3], os2 = it.out_strides[2];
+    const int tk = K / 64, tn = N / 64;
+    const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;   // load: 16 threads x float4 per row, 16 rows per pass
+    const int sx = threadIdx.x & 31, sy = threadIdx.x >> 5;   // store: 32 threads x bf16 pair per row, 8 rows per pass
+    for (int t = blockIdx.x; t < tk * tn; t += gridDim.x) {
+        const int k0 = (t % tk) * 64, n0 = (t / tk) * 64;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int n = ly + 16 * r;
+            const float4 v = *reinterpret_cast<const float4*>(in + (long long)(n0 + n) * is3 + k0 + 4 * lx);
+            tile[n][4 * lx + 0] = v.x;
+            tile[n][4 * lx + 1] = v.y;
+            tile[n][4 * lx + 2] = v.z;
+            tile[n][4 * lx + 3] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int k = sy + 8 * r;
+            const uint32_t pk = pack_bf16x2(tile[2 * sx][k], tile[2 * sx + 1][k]);
+            *reinterpret_cast<uint32_t*>(out + (long long)(k0 + k) * os2 + n0 + 2 * sx) = pk;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(256) relayout_batch_kernel(const a2v_relayout_item* __restrict__ items) {
     __shared__ a2v_relayout_item it;
-    __shared__ float tile[32][33];
+    __shared__ __align__(16) float tile_raw[64 * 65];
+    float (*tile)[33] = reinterpret_cast<float (*)[33]>(tile_raw);
     if (threadIdx.x == 0) it = items[blockIdx.y];
     __syncthreads();
+    if (it.dims[0] == 1 && it.dims[1] == 1 && it.in_strides[2] == 1 && it.out_strides[3] == 1 && !it.zero_src &&
+        !it.accumulate && it.in_dtype == A2V_F32 && it.out_dtype == A2V_BF16 && it.dims[2] % 64 == 0 &&
+        it.dims[3] % 64 == 0 && it.in_strides[3] % 4 == 0 && it.in_offset % 4 == 0 && it.out_strides[2] % 2 == 0 &&
+        it.out_offset % 2 == 0 && (reinterpret_cast<uintptr_t>(it.in) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(it.out) & 3) == 0) {
+        relayout_item_transpose64(it, reinterpret_cast<float (*)[65]>(tile_raw));
+        return;
+    }
     if (it.dims[0] == 1 && it.dims[1] == 1 && it.in_strides[2] == 1 && it.out_strides[3] == 1 && !it.zero_src &&
         it.dims[2] >= 32 && it.dims[3] >= 32) {
         if (it.in_dtype == A2V_F32 && it.out_dtype == A2V_BF16) { relayout_item_transpose<float, bf16>(it, tile); return; }

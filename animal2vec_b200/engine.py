@@ -383,12 +383,15 @@ class PretrainEngine:
             a = self._split_a(a, (W.split_d if dgrad else W.split)[name])
         return gemm.gemm_nt(a, w, out_dtype=self.adt, **kw)
 
-    def conv(self, x, W: _Weights, name, *, taps, pad, groups, dgrad=False, bias=None):
+    def conv(self, x, W: _Weights, name, *, taps, pad, groups, dgrad=False, bias=None, x_real=0):
+        """``x_real``: channels per 64-wide input group that can be non-zero (the group-padded decoder layout keeps
+        dec_ng of 64): the slab kernel skips the K steps over the padding."""
         w = (W.dgrad if dgrad else W.fwd)[name]
         if self.fp32:
             x = self._split_a(x, (W.split_d if dgrad else W.split)[name])
         elif gemm.conv_slab_ok(x, w, taps, groups):
-            return gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias)
+            return gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias,
+                                  x_real_cols=x_real)
         return gemm.conv_nt(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias)
 
     def wgrad(self, dy, x, out):
@@ -567,7 +570,7 @@ class PretrainEngine:
         for l in range(dc.decoder_layers):
             n = ENC + f"decoder.blocks.{l}.0.weight"
             y = self.conv(x, W, n, taps=dc.decoder_kernel, pad=dc.decoder_kernel // 2, groups=dc.decoder_groups,
-                          bias=W.f32[ENC + f"decoder.blocks.{l}.0.bias"])
+                          bias=W.f32[ENC + f"decoder.blocks.{l}.0.bias"], x_real=0 if l == 0 else self.dec_ng)
             res = x if l > 0 else None  # layer 0 changes the channel count: no residual
             act, m, r = ops.rowln_fwd(cfg_l, y, post=res, save_stats=save is not None)
             if save is not None:
@@ -797,7 +800,7 @@ class PretrainEngine:
             self.conv_wgrad(dy, s.x, self.gpacked[n + "|F"], taps=dc.decoder_kernel, pad=dc.decoder_kernel // 2,
                             groups=dc.decoder_groups)
             dxin = self.conv(dy, W, n, taps=dc.decoder_kernel, pad=dc.decoder_kernel - 1 - dc.decoder_kernel // 2,
-                             groups=dc.decoder_groups, dgrad=True)
+                             groups=dc.decoder_groups, dgrad=True, x_real=self.dec_ng)
             if s.res:  # y = act(...) + x: the residual passes dx straight through
                 dxin = self._add(dxin, dx)
             dx = dxin

@@ -351,8 +351,9 @@ def conv_slab_ok(x: torch.Tensor, w: torch.Tensor, taps: int, groups: int) -> bo
 
 def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: int,
               out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-              bias: Optional[torch.Tensor] = None, _bo_mode: int = 0) -> torch.Tensor:
-    """Same operator as :func:`conv_nt` (64-channel groups), every activation row read once per tile."""
+              bias: Optional[torch.Tensor] = None, x_real_cols: int = 0) -> torch.Tensor:
+    """Same operator as :func:`conv_nt` (64-channel groups), every activation row read once per tile. ``x_real_cols``:
+    channels per 64-wide input group that can be non-zero (group-padded layouts); the K steps over the rest are skipped."""
     bsz, t, cin = x.shape
     assert x.is_contiguous() and w.is_contiguous() and w.dtype == torch.bfloat16
     nout = w.shape[0]
@@ -367,7 +368,7 @@ def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: 
     d.ldx, d.ldw, d.ldy = cin, w.shape[1], nout
     d.y_dtype = L.dtype_code(out)
     d.bias = bias.data_ptr() if bias is not None else None
-    d.reserved = _bo_mode
+    d.x_real_cols = x_real_cols
     L.require_device(x)
     L.launch_count += 1
     tl = L.gemm_timeline

@@ -112,7 +112,7 @@ class ConvDesc(C.Structure):
         ("ldy", C.c_int64),
         ("y_dtype", C.c_int),
         ("bias", C.c_void_p),
-        ("reserved", C.c_int),
+        ("x_real_cols", C.c_int),
     ]
 
 

@@ -136,7 +136,8 @@ typedef struct {
     int64_t ldx, ldw, ldy;
     int y_dtype;
     const float* bias;    /* per global y column, or NULL */
-    int reserved;         /* 0 */
+    int x_real_cols;      /* conv_slab_fwd: channels of each 64-wide input group that can be non-zero (0 = all 64);
+                             the K steps over the rest are skipped (group-padded decoder layout: 48 of 64) */
 } a2v_conv_desc;
 
 int a2v_conv_slab_supported(const a2v_conv_desc* d);

@@ -139,6 +139,25 @@ def test_conv_slab(bsz, t, ng, groups, taps, pad):
     assert _rel(out16, ref) < 5e-3
 
 
+@pytest.mark.parametrize("real", [16, 48])
+def test_conv_slab_skips_the_zero_padded_channels_of_a_group(real):
+    """Group-padded layout (the decoder: 48 real channels in 64-wide groups, zero weights over the padding): with
+    ``x_real_cols`` the kernel skips the K steps over the padding -- same result whatever the padding columns hold."""
+    from animal2vec_b200 import gemm
+
+    bsz, t, groups, taps, pad, cg = 2, 300, 4, 7, 3, 64
+    x = _randn(bsz, t, groups * cg, seed=21)
+    wt = _randn(groups * 64, cg, taps, scale=0.05, seed=22)
+    wt.view(groups, 64, cg, taps)[:, :, real:] = 0
+    ref = F.conv1d(x.float().transpose(1, 2), wt.float(), None, padding=pad, groups=groups).transpose(1, 2)
+    w = wt.permute(0, 2, 1).reshape(groups * 64, taps * cg).contiguous()
+    full = gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=torch.float32)
+    xg = x.clone()
+    xg.view(bsz, t, groups, cg)[..., real:] = 1.0e4  # finite garbage in the padding columns
+    skip = gemm.conv_slab(xg, w, taps=taps, pad=pad, groups=groups, out_dtype=torch.float32, x_real_cols=real)
+    assert _rel(full, ref) < 1e-5 and _rel(skip, ref) < 1e-5, (_rel(full, ref), _rel(skip, ref))
+
+
 @pytest.mark.parametrize("bsz,t,ng,groups,taps,pad", [(2, 300, 64, 4, 19, 9), (3, 130, 64, 2, 7, 3), (2, 2000, 64, 16, 19, 9),
                                                        (2, 257, 48, 3, 7, 3), (5, 64, 64, 1, 3, 1), (1, 700, 64, 2, 25, 12)])
 def test_conv_slab_wgrad(bsz, t, ng, groups, taps, pad):

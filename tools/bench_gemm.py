@@ -64,10 +64,10 @@ def main():
     print(res[-1], flush=True)
     for mode in (0,):
         try:
-            o2 = gemm.conv_slab(x, w, taps=19, pad=9, groups=16, _bo_mode=mode)
+            o2 = gemm.conv_slab(x, w, taps=19, pad=9, groups=16)
             err = ((o2.float() - out.float()).norm() / out.float().norm()).item()
-            ms = bench(lambda: gemm.conv_slab(x, w, taps=19, pad=9, groups=16, out=o2, _bo_mode=mode))
-            res.append({"op": f"conv_slab(bo_mode={mode})", "ms": ms, "tflops": fl / ms / 1e9, "rel_vs_conv_nt": err})
+            ms = bench(lambda: gemm.conv_slab(x, w, taps=19, pad=9, groups=16, out=o2))
+            res.append({"op": "conv_slab", "ms": ms, "tflops": fl / ms / 1e9, "rel_vs_conv_nt": err})
             print(res[-1], flush=True)
         except Exception as ex:
             print("conv_slab failed", mode, ex, flush=True)
