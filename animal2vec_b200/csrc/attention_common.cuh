@@ -34,24 +34,6 @@ struct AttnParams {
     int head_filter;        // flash forward: 1 = only the heads attention_stream.cu declined (attn_stream_head_ok false)
 };
 
-// Column sums over the 32 lanes of a warp for N columns held per lane (N = 16 or 32): a transposing butterfly, N - 1
-// (+1 for N = 16) shuffles instead of 5 N. Afterwards v[0] of lane l is the sum of column l % N over all 32 lanes.
-template <int N>
-__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane) {
-#pragma unroll
-    for (int s = N / 2; s >= 1; s >>= 1) {
-        const bool upper = (lane & s) != 0;
-#pragma unroll
-        for (int k = 0; k < s; ++k) {
-            const float send = upper ? v[k] : v[k + s];
-            const float keep = upper ? v[k + s] : v[k];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    if (N == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
-    return v[0];
-}
-
 __device__ __forceinline__ float head_coef(const AttnParams& p, int h) {
     float sc = 1.0f;
     if (p.alibi_scale != nullptr) sc = fmaxf(p.alibi_scale[h * p.alibi_scale_stride], 0.f);

@@ -33,7 +33,7 @@ constexpr int G2_EPI_PITCH = 80;
 constexpr int G2_EPI_BYTES = 8 * 32 * G2_EPI_PITCH;
 constexpr int G2_BIAS_BYTES = 8 * 128 * 4;
 constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_BAR_BYTES + G2_EPI_BYTES + G2_BIAS_BYTES + 1024;
-constexpr int G2_EPI_BIAS = 1, G2_EPI_PREACT = 2, G2_EPI_GELU = 4, G2_EPI_RES = 16;
+constexpr int G2_EPI_BIAS = 1, G2_EPI_PREACT = 2, G2_EPI_GELU = 4, G2_EPI_DGELU = 8, G2_EPI_RES = 16;
 
 struct Gemm2Params {
     int M, N, kblocks;
@@ -43,7 +43,8 @@ struct Gemm2Params {
     float alpha;
     const float* bias;
     void* preact;
-    const void* residual;
+    const void* residual;  // G2_EPI_RES: added; G2_EPI_DGELU: u, the result is multiplied by GELU'(u)
+    float* colsum;         // optional (G2_EPI_DGELU): += column sums of the result (the bias gradient of the Linear before)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -219,7 +220,8 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 *reinterpret_cast<float4*>(bs + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + lane);
                 __syncwarp();
             }
-            constexpr bool RES = (EPI & G2_EPI_RES) != 0;
+            constexpr bool DGELU = (EPI & G2_EPI_DGELU) != 0;
+            constexpr bool RES = (EPI & (G2_EPI_RES | G2_EPI_DGELU)) != 0;  // a second (M, N) bf16 operand, prefetched under the MMAs
             uint4 rsd[RES ? CPW : 1][4];
             if (RES) {
                 const bf16* rp = reinterpret_cast<const bf16*>(p.residual) + row_off0 + (long long)lane * p.ldc + cbase;
@@ -254,9 +256,25 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint4 rv = rsd[RES ? cc : 0][j];
                         const float2 r0 = unpack_bf16x2(rv.x), r1 = unpack_bf16x2(rv.y);
                         const float2 r2 = unpack_bf16x2(rv.z), r3 = unpack_bf16x2(rv.w);
-                        x[8 * j] += r0.x; x[8 * j + 1] += r0.y; x[8 * j + 2] += r1.x; x[8 * j + 3] += r1.y;
-                        x[8 * j + 4] += r2.x; x[8 * j + 5] += r2.y; x[8 * j + 6] += r3.x; x[8 * j + 7] += r3.y;
+                        if (DGELU) {  // backward of the activation between two Linears: dh * GELU'(u)
+                            x[8 * j] *= gelu_tanh_fast_grad(r0.x); x[8 * j + 1] *= gelu_tanh_fast_grad(r0.y);
+                            x[8 * j + 2] *= gelu_tanh_fast_grad(r1.x); x[8 * j + 3] *= gelu_tanh_fast_grad(r1.y);
+                            x[8 * j + 4] *= gelu_tanh_fast_grad(r2.x); x[8 * j + 5] *= gelu_tanh_fast_grad(r2.y);
+                            x[8 * j + 6] *= gelu_tanh_fast_grad(r3.x); x[8 * j + 7] *= gelu_tanh_fast_grad(r3.y);
+                        } else {
+                            x[8 * j] += r0.x; x[8 * j + 1] += r0.y; x[8 * j + 2] += r1.x; x[8 * j + 3] += r1.y;
+                            x[8 * j + 4] += r2.x; x[8 * j + 5] += r2.y; x[8 * j + 6] += r3.x; x[8 * j + 7] += r3.y;
+                        }
                     }
+                }
+                if (DGELU && p.colsum != nullptr) {
+                    // column sums of the result (before its bf16 rounding) over this warp's 32 rows: transposing
+                    // butterfly, then one 32-lane vector of atomic adds per chunk
+                    float cs[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) cs[i] = lane < rows_ok ? x[i] : 0.f;
+                    const float tot = warp_colsum<32>(cs, lane);
+                    atomicAdd(p.colsum + col0 + lane, tot);
                 }
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -589,24 +607,28 @@ static int g2_try_tn(const a2v_gemm_desc* d, cudaStream_t st) {
 int gemm2cta_try(const a2v_gemm_desc* d, cudaStream_t st) {
     if (d->mode == 1) return g2_try_tn(d, st);
     if (d->mode != 0 || d->taps != 1 || d->batch != 1 || d->groups != 1 || d->c_dtype != A2V_BF16) return -1;
-    if (d->out_atomic || d->out_accumulate || d->dgelu_u != nullptr) return -1;
+    if (d->out_atomic || d->out_accumulate) return -1;
+    if (d->dgelu_u != nullptr && (d->bias || d->preact || d->residual || d->act != 0)) return -1;
+    if (d->colsum != nullptr && d->dgelu_u == nullptr) return -1;
     if (d->block_n != 256 || d->N % G2_BN != 0 || d->k_per_tap % G2_BK != 0 || d->M < 4 * G2_BM) return -1;
     if (d->a_row_off != 0 || d->b_row_off != 0 || d->c_row_off != 0 || d->ldc % 8 != 0) return -1;
     if (d->a.dim2 != 1 || d->b.dim2 != 1 || d->a.stride1 % 8 != 0 || d->b.stride1 % 8 != 0) return -1;
     const uintptr_t al = reinterpret_cast<uintptr_t>(d->a.ptr) | reinterpret_cast<uintptr_t>(d->b.ptr) |
                          reinterpret_cast<uintptr_t>(d->c) | reinterpret_cast<uintptr_t>(d->bias) |
-                         reinterpret_cast<uintptr_t>(d->preact) | reinterpret_cast<uintptr_t>(d->residual);
+                         reinterpret_cast<uintptr_t>(d->preact) | reinterpret_cast<uintptr_t>(d->residual) |
+                         reinterpret_cast<uintptr_t>(d->dgelu_u);
     if (al & 15) return -1;
     const int m = (d->bias ? G2_EPI_BIAS : 0) | (d->preact ? G2_EPI_PREACT : 0) | (d->act == 1 ? G2_EPI_GELU : 0) |
-                  (d->residual ? G2_EPI_RES : 0);
-    if (!(m == 0 || m == 1 || m == 5 || m == 7 || m == 16)) return -1;
+                  (d->residual ? G2_EPI_RES : 0) | (d->dgelu_u ? G2_EPI_DGELU : 0);
+    if (!(m == 0 || m == 1 || m == 5 || m == 7 || m == 8 || m == 16)) return -1;
     if (d->act != 0 && d->act != 1) return -1;
     Gemm2Params p;
     memset(&p, 0, sizeof(p));
     p.M = d->M; p.N = d->N; p.kblocks = d->k_per_tap / G2_BK;
     p.n_tiles = d->N / G2_BN;
     p.num_tiles = p.n_tiles * ceil_div(d->M, 2 * G2_BM);
-    p.c = d->c; p.ldc = d->ldc; p.alpha = d->alpha; p.bias = d->bias; p.preact = d->preact; p.residual = d->residual;
+    p.c = d->c; p.ldc = d->ldc; p.alpha = d->alpha; p.bias = d->bias; p.preact = d->preact; p.residual = d->dgelu_u ? d->dgelu_u : d->residual;
+    p.colsum = d->colsum;
     CUtensorMap ta, tb;
     if (g2_make_map(&ta, d->a) != 0 || g2_make_map(&tb, d->b) != 0) return -1;
     switch (m) {
@@ -614,6 +636,7 @@ int gemm2cta_try(const a2v_gemm_desc* d, cudaStream_t st) {
         case 1: return g2_launch<1>(ta, tb, p, st);
         case 5: return g2_launch<5>(ta, tb, p, st);
         case 7: return g2_launch<7>(ta, tb, p, st);
+        case 8: return g2_launch<8>(ta, tb, p, st);
         default: return g2_launch<16>(ta, tb, p, st);
     }
 }

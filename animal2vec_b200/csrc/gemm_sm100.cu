@@ -724,6 +724,8 @@ extern "C" int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream) {
         const int rc2 = gemm2cta_try(d, reinterpret_cast<cudaStream_t>(stream));
         if (rc2 >= 0) return rc2;
     }
+    A2V_REQUIRE(d->colsum == nullptr, "gemm: the fused column-sum epilogue exists for the CTA-pair Linear shapes only "
+                                      "(bf16, N %% 256 == 0, K %% 64 == 0, M >= 512, A2V_GEMM_2CTA on)");
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.mode = d->mode;

@@ -15,6 +15,7 @@ validation mode used for the 1e-3 per-stage parity gate.
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence
 
@@ -751,10 +752,17 @@ class PretrainEngine:
                 dt = self._add(dt, extra_dt)
                 ops.colsum(dt, G(pre + "mlp.fc2.bias"))
         self.wgrad(dt, s.h, G(pre + "mlp.fc2.weight"))
-        dh = self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True)
-        if getattr(s, "p_mlp", 0.0) > 0:
-            dh = ops.row_gather(dh, self._arange(rows * seq), rows * seq, drop_p=s.p_mlp, drop_seed=s.s_mlp)
-        du = ops.dgelu_mul(dh, s.u, colsum=G(pre + "mlp.fc1.bias"))
+        p_mlp = getattr(s, "p_mlp", 0.0)
+        if not self.fp32 and p_mlp == 0 and gemm.pair_shape_ok(dt.numel() // dt.shape[-1], s.u.shape[-1], dt.shape[-1],
+                                                               dt.dtype):
+            # GELU backward and the fc1 bias gradient ride in the epilogue of the fc2 data-gradient product
+            du = self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True, dgelu_u=s.u.view(*dt.shape[:-1], -1),
+                          colsum=G(pre + "mlp.fc1.bias"))
+        else:
+            dh = self.lin(dt, W, pre + "mlp.fc2.weight", dgrad=True)
+            if p_mlp > 0:
+                dh = ops.row_gather(dh, self._arange(rows * seq), rows * seq, drop_p=s.p_mlp, drop_seed=s.s_mlp)
+            du = ops.dgelu_mul(dh, s.u, colsum=G(pre + "mlp.fc1.bias"))
         self.wgrad(du, s.x1, G(pre + "mlp.fc1.weight"))
         dx1 = self.lin(du, W, pre + "mlp.fc1.weight", dgrad=True, residual=dz2)
         del du, dz2, dt

@@ -81,13 +81,15 @@ def gemm_nt(
     preact: Optional[torch.Tensor] = None,
     residual: Optional[torch.Tensor] = None,
     dgelu_u: Optional[torch.Tensor] = None,
+    colsum: Optional[torch.Tensor] = None,
     alpha: float = 1.0,
     accumulate: bool = False,
     block_n: Optional[int] = None,
 ) -> torch.Tensor:
     """out[m, n] = alpha * sum_k a[m, k] * w[n, k] (+bias[n]) -> GELU -> *GELU'(u) -> +residual.
 
-    ``a``: (..., K) bf16, ``w``: (N, K) bf16 (nn.Linear weight layout).
+    ``a``: (..., K) bf16, ``w``: (N, K) bf16 (nn.Linear weight layout). ``colsum`` (fp32 (N), with ``dgelu_u`` on the
+    shapes :func:`pair_shape_ok` accepts): += column sums of the result.
     """
     m, k, lda = _rows2d(a)
     n, kw, ldb = _rows2d(w)
@@ -119,8 +121,18 @@ def gemm_nt(
     d.preact = preact.data_ptr() if preact is not None else None
     d.residual = residual.data_ptr() if residual is not None else None
     d.dgelu_u = dgelu_u.data_ptr() if dgelu_u is not None else None
+    if colsum is not None:
+        assert colsum.dtype == torch.float32 and colsum.numel() == n and colsum.is_contiguous() and dgelu_u is not None
+        d.colsum = colsum.data_ptr()
     _launch(d, a)
     return out
+
+
+def pair_shape_ok(m: int, n: int, k: int, dtype: torch.dtype = torch.bfloat16) -> bool:
+    """Plain Linear shapes the CTA-pair kernels (gemm2_sm100.cu) take; the fused column-sum epilogue exists only there."""
+    import os
+    return (dtype == torch.bfloat16 and n % 256 == 0 and k % 64 == 0 and m >= 512 and
+            os.environ.get("A2V_GEMM_2CTA", "1")[:1] != "0")
 
 
 def conv_nt(

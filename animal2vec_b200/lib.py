@@ -90,6 +90,7 @@ class GemmDesc(C.Structure):
         ("a_grow_add", C.c_int),
         ("a_grow_div", C.c_int),
         ("a_tap_col_stride", C.c_int),
+        ("colsum", C.c_void_p),
     ]
 
 

@@ -113,6 +113,10 @@ typedef struct {
      * a_row_off = 0, a_tap_col_stride = C, groups select 64-channel slices inside each tap block (the last positional-conv
      * layer evaluated only on the rows the student keeps, nn/modalities/base.py:278-280). */
     int a_tap_col_stride;
+    /* optional, with dgelu_u on a plain bf16 Linear product: += column sums of the stored result, fp32 (N) -- the bias
+     * gradient of the Linear in front of the activation (timm Mlp.fc1, nn/modalities/modules.py:312-317), so the
+     * activation backward needs no pass of its own */
+    float* colsum;
 } a2v_gemm_desc;
 
 int a2v_gemm(const a2v_gemm_desc* d, a2v_stream_t stream);

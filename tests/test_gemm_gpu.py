@@ -177,6 +177,26 @@ def test_conv_slab_wgrad(bsz, t, ng, groups, taps, pad):
     assert _rel(out, 2 * ref) < 1e-5
 
 
+@pytest.mark.parametrize("m,n,k", [(600, 256, 128), (1500, 512, 320), (4100, 4096, 1024)])
+def test_cta_pair_gemm_fused_gelu_backward_and_column_sums(m, n, k):
+    """Epilogue of the fc2 data-gradient product: result * GELU'(u) with the column sums of the stored result (= the fc1
+    bias gradient) accumulated on top of what the buffer holds; ragged M (rows beyond M must not reach the sums)."""
+    from animal2vec_b200 import gemm
+
+    a, w = _randn(m, k, seed=31), _randn(n, k, scale=0.05, seed=32)
+    u = _randn(m, n, seed=33)
+    uf = u.float().requires_grad_(True)
+    F.gelu(uf, approximate="tanh").sum().backward()
+    ref = (a.float() @ w.float().t()) * uf.grad
+    acc = torch.full((n,), 0.5, device="cuda")
+    assert gemm.pair_shape_ok(m, n, k)
+    out = gemm.gemm_nt(a, w, dgelu_u=u, colsum=acc)
+    assert _rel(out, ref) < 5e-3, _rel(out, ref)
+    assert _rel(acc, 0.5 + ref.sum(0)) < 2e-3, _rel(acc, 0.5 + ref.sum(0))  # fp32 sums of the unrounded products
+    plain = gemm.gemm_nt(a, w, dgelu_u=u)
+    assert torch.equal(plain, out)
+
+
 @pytest.mark.parametrize("m,n,k", [(513, 256, 64), (1500, 512, 320), (4000, 1024, 1024)])
 def test_cta_pair_gemm_shapes_and_epilogues(m, n, k):
     """Shapes the CTA-pair (cta_group::2) kernels take (N a multiple of 256, K of 64): ragged M (the second CTA of the last
