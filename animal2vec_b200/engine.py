@@ -15,7 +15,6 @@ validation mode used for the 1e-3 per-stage parity gate.
 from __future__ import annotations
 
 import math
-import os
 from types import SimpleNamespace
 from typing import Dict, List, Optional, Sequence
 
