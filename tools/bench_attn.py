@@ -22,7 +22,7 @@ B = int(os.environ.get("B", "16"))
 H = 16
 slopes = torch.tensor([2.0 ** (-0.5 * (h + 1)) for h in range(H)], device="cuda")
 scale = torch.ones(H, device="cuda")
-for name, batch, L, with_pos, drop in [("teacher", B, 2000, False, 0.0), ("student", B * 12, 142, True, 0.1),
+for name, batch, L, with_pos, drop in [("teacher", B, 2000, False, 0.0), ("long12000", max(1, B // 8), 12000, False, 0.0), ("student", B * 12, 142, True, 0.1),
                                        ("student148", B * 12, 148, True, 0.1), ("student128", B * 12, 128, True, 0.1)]:
     if os.environ.get("ONLY") and os.environ["ONLY"] not in name:
         continue
