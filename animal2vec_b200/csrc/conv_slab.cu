@@ -15,8 +15,9 @@
 // shifted down by j rows (descriptor start address + j*128 B; the 128B swizzle is a function of the
 // absolute shared-memory address, so the shifted view stays consistent with what TMA wrote). Two 128-row output tiles
 // share each weight tile. Warp roles: warp 0 slab producer (4-stage ring: the activations stream from HBM once, the
-// producer runs tiles ahead), warp 6 weight-tile producer (6-stage ring, L2 resident), warp 1 tcgen05.mma issuer (one
-// thread), warps 2..5 epilogue out of double-buffered TMEM accumulators.
+// producer runs tiles ahead), warp 10 weight-tile producer (6-stage ring, L2 resident), warp 1 tcgen05.mma issuer (one
+// thread), warps 2..9 epilogue out of double-buffered TMEM accumulators (one 128-row tile per warpgroup: with four
+// epilogue warps the 7-tap layers were bound by the epilogue's serial chunk loop, not by the tensor pipe or HBM).
 #include <string.h>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
@@ -27,16 +28,18 @@ constexpr int CS_BLOCK_M = 128;
 constexpr int CS_MT = 2;                        // 128-row tiles per slab
 constexpr int CS_SUPER_M = CS_BLOCK_M * CS_MT;  // output rows per tile
 constexpr int CS_NB = 6;                        // weight-tile ring stages (8 KB each)
-constexpr int CS_NS = 4;                        // slab ring stages: a slab comes from HBM (the activations are streamed once),
-                                                // two stages left the tensor pipe waiting on the load of the tile after next
+constexpr int CS_NS = 3;                        // slab ring stages (a slab comes from HBM: the activations are streamed once)
 constexpr int CS_B_BYTES = 64 * 64 * 2;
 constexpr int CS_THREADS = 192;
-constexpr int CS_FWD_THREADS = 224;             // forward: + warp 6, the weight-tile producer
+constexpr int CS_FWD_THREADS = 352;             // forward: 8 epilogue warps (2..9, one 128-row tile each) + warp 10, the weight-tile producer
 constexpr int CS_EPI_PITCH = 36;
 constexpr int CS_EPI_BYTES = 4 * 32 * CS_EPI_PITCH * 4;
+constexpr int CS_FWD_EPI_BYTES = 2 * CS_EPI_BYTES;  // forward: 8 epilogue warps
 
 struct ConvSlabParams {
     int batch, T, groups, taps, pad, ng;
+    int x_group_cols;  // channel distance between the groups of x (64; 48 for the compact decoder layout: the 64-wide box
+                       // then overlaps the next group, whose channels only meet skipped K steps)
     int w_group_rows, y_group_cols;
     long long ldy;
     void* y;
@@ -118,7 +121,7 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], 8);
         }
         for (int i = 0; i < CS_NB; ++i) {
             mbar_init(&b_full[i], 1);
@@ -159,13 +162,13 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 uint8_t* slab = slab0 + ss * slab_bytes;
                 mbar_expect_tx(&slab_full[ss], (uint32_t)slab_bytes);
                 const int r0 = ms * CS_SUPER_M - p.pad;
-                tma_load_3d(slab, &tmX, &slab_full[ss], g * 64, r0, b);
-                tma_load_3d(slab + half_rows * 128, &tmX, &slab_full[ss], g * 64, r0 + half_rows, b);
+                tma_load_3d(slab, &tmX, &slab_full[ss], g * p.x_group_cols, r0, b);
+                tma_load_3d(slab + half_rows * 128, &tmX, &slab_full[ss], g * p.x_group_cols, r0 + half_rows, b);
                 if (++ss == CS_NS) { ss = 0; sphase ^= 1; }
             }
         }
         __syncwarp();
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // weight-tile producer
         if (elect_one()) {
             int bs = 0;
@@ -228,8 +231,8 @@ conv_slab_fwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             decode(tile, ms, b, g);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < CS_MT; ++mt) {
+            {
+                const int mt = (warp - 2) >> 2;  // warps 2..5: rows 0..127 of the tile, warps 6..9: rows 128..255
                 const int row0 = ms * CS_SUPER_M + mt * CS_BLOCK_M + q * 32;
                 int rows_ok = p.T - row0;
                 rows_ok = rows_ok > 32 ? 32 : rows_ok;
@@ -335,6 +338,7 @@ constexpr int CW_STAGE_BYTES = CW_SLAB_BYTES + CW_DY_BYTES;
 
 struct ConvWgradParams {
     int batch, T, groups, taps, pad, ng;
+    int x_group_cols;  // as in ConvSlabParams; the M rows of the overlap (channels >= x_group_cols) are scratch rows of `out`
     int dy_group_cols;
     float* out;          // (groups*taps*64, ldo) fp32
     long long ldo;
@@ -401,7 +405,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sx = smem + stage * CW_STAGE_BYTES;
                 mbar_expect_tx(&full_bar[stage], CW_STAGE_BYTES);
-                tma_load_3d(sx, &tmX, &full_bar[stage], g * 64, r0 + tb * 16 - p.pad, b);
+                tma_load_3d(sx, &tmX, &full_bar[stage], g * p.x_group_cols, r0 + tb * 16 - p.pad, b);
                 tma_load_3d(sx + CW_SLAB_BYTES, &tmDy, &full_bar[stage], g * p.dy_group_cols, r0, b);
                 if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -525,8 +529,13 @@ static int cs_make_map(CUtensorMap* m, const void* ptr, long long cols, long lon
 using namespace a2v;
 
 extern "C" int a2v_conv_slab_supported(const a2v_conv_desc* d) {
+    // x_group_cols < 64 (compact group-padded layouts): the 64-channel box overlaps the next group, so the caller must
+    // declare x_real_cols <= x_group_cols -- the K steps over the overlap are then never issued (forward), or land in
+    // scratch rows of the output (weight gradient)
     return d != nullptr && d->taps >= 1 && d->taps <= 32 && d->ng >= 1 && d->ng <= 64 && d->ldx % 8 == 0 &&
-           d->x_group_cols == 64 && d->T >= 1 && d->pad >= 0 && d->pad < d->taps;
+           (d->x_group_cols == 64 || (d->x_group_cols >= 16 && d->x_group_cols < 64 && d->x_group_cols % 16 == 0 &&
+                                      d->x_real_cols > 0 && d->x_real_cols <= d->x_group_cols)) &&
+           d->T >= 1 && d->pad >= 0 && d->pad < d->taps;
 }
 
 extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
@@ -541,7 +550,7 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     ConvSlabParams p;
     memset(&p, 0, sizeof(p));
     p.batch = d->batch; p.T = d->T; p.groups = d->groups; p.taps = d->taps; p.pad = d->pad; p.ng = d->ng;
-    p.w_group_rows = d->w_group_rows; p.y_group_cols = d->y_group_cols;
+    p.x_group_cols = d->x_group_cols; p.w_group_rows = d->w_group_rows; p.y_group_cols = d->y_group_cols;
     p.ldy = d->ldy; p.y = d->y; p.y_f32 = d->y_dtype == A2V_F32; p.bias = d->bias;
     p.slab_rows = (CS_SUPER_M + d->taps - 1 + 15) & ~15;
     p.m_tiles = ceil_div(d->T, CS_SUPER_M);
@@ -549,6 +558,7 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     A2V_REQUIRE(d->x_real_cols >= 0 && d->x_real_cols <= 64, "conv_slab: x_real_cols out of range");
     // K steps of 16 channels per tap: 3 when the last 16 channels of every input group are zero padding, else 4
     const int ksteps = (d->x_real_cols > 0 && d->x_real_cols <= 48) ? 3 : 4;
+    A2V_REQUIRE(d->x_group_cols == 64 || ksteps * 16 <= d->x_group_cols, "conv_slab: compact groups need K steps inside the group (x_group_cols %d, %d steps)", d->x_group_cols, ksteps);
     p.fast_store = !p.y_f32 && d->ng % 8 == 0 && d->ldy % 8 == 0 && d->y_group_cols % 8 == 0 &&
                    (reinterpret_cast<uintptr_t>(d->y) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0;
     CUtensorMap tx, tw;
@@ -556,7 +566,7 @@ extern "C" int a2v_conv_slab_fwd(const a2v_conv_desc* d, a2v_stream_t stream) {
     if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, p.slab_rows / 2, "x")) != A2V_OK) return rc;
     if ((rc = cs_make_map(&tw, d->w, d->ldw, (long long)d->groups * d->w_group_rows, 1, d->ldw, 64, "w")) != A2V_OK)
         return rc;
-    const int smem = CS_NS * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_EPI_BYTES + 1024;
+    const int smem = CS_NS * p.slab_rows * 128 + CS_NB * CS_B_BYTES + 256 + CS_FWD_EPI_BYTES + 1024;
     const int grid = p.num_tiles < a2v_num_sms() ? p.num_tiles : a2v_num_sms();
     if (ksteps == 3) {
         if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_fwd_kernel<3>), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
@@ -577,6 +587,7 @@ extern "C" int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t l
     ConvWgradParams p;
     memset(&p, 0, sizeof(p));
     p.batch = d->batch; p.T = d->T; p.groups = d->groups; p.taps = d->taps; p.pad = d->pad; p.ng = d->ng;
+    p.x_group_cols = d->x_group_cols;
     p.dy_group_cols = d->w_group_rows;
     p.out = out; p.ldo = ldo;
     p.kb_per_batch = ceil_div(d->T, 64);

@@ -270,7 +270,12 @@ class PretrainEngine:
         if self.dec_ng > GP or (d // dg) % 64 or (d // a.conv_pos_groups) % 64 or dc.decoder_dim == d:
             raise NotImplementedError("channel-group widths: embed_dim/groups must be a multiple of 64, decoder "
                                       "groups at most 64 wide and decoder_dim != embed_dim")
-        self.dec_wp = dg * GP  # stored decoder width
+        # bf16: compact storage (dec_ng channels per group, nothing between the groups) -- the slab kernels address the
+        # groups dec_ng apart and skip the K steps over what would be padding; the decoder layers are HBM bound, the
+        # padding was a quarter of their bytes. The weight packs keep GP-wide K / N blocks either way. fp32 validation
+        # mode: GP-wide groups (its tap-loop GEMM needs 64-channel groups).
+        self.dec_gw = self.dec_ng if (not self.fp32 and self.dec_ng == 48) else GP
+        self.dec_wp = dg * self.dec_gw  # stored decoder width
         for l in range(dc.decoder_layers):
             n = ENC + f"decoder.blocks.{l}.0.weight"
             cg = (d // dg) if l == 0 else self.dec_ng
@@ -278,10 +283,10 @@ class PretrainEngine:
             sp[n + "|F"] = P.pack_conv_fwd(n, dg, self.dec_ng, cg, dc.decoder_kernel, ngp=GP, cgp=cgp)
             sp[n + "|T"] = P.pack_conv_dgrad(n, dg, self.dec_ng, cg, dc.decoder_kernel, ngp=GP, cgp=cgp)
             sp[ENC + f"decoder.blocks.{l}.0.bias|B"] = P.pack_bias_padded(ENC + f"decoder.blocks.{l}.0.bias", dg,
-                                                                          self.dec_ng, GP)
+                                                                          self.dec_ng, self.dec_gw)
         n = ENC + "decoder.proj.weight"
-        sp[n + "|F"] = P.pack_cols_padded(n, d, dg, self.dec_ng, GP)
-        sp[n + "|T"] = P.pack_cols_padded_t(n, d, dg, self.dec_ng, GP)
+        sp[n + "|F"] = P.pack_cols_padded(n, d, dg, self.dec_ng, self.dec_gw)
+        sp[n + "|T"] = P.pack_cols_padded_t(n, d, dg, self.dec_ng, self.dec_gw)
         self.sp, self.tp = sp, tp
         # packed fp32 gradient buffers for weights whose GEMM layout differs from the checkpoint layout
         # (tap convs: TRANSPOSED layout (G*k*Cg, Ng) written by gemm.conv_wgrad_tn, see params.pack_conv_fwd)
@@ -383,15 +388,17 @@ class PretrainEngine:
             a = self._split_a(a, (W.split_d if dgrad else W.split)[name])
         return gemm.gemm_nt(a, w, out_dtype=self.adt, **kw)
 
-    def conv(self, x, W: _Weights, name, *, taps, pad, groups, dgrad=False, bias=None, x_real=0):
-        """``x_real``: channels per 64-wide input group that can be non-zero (the group-padded decoder layout keeps
-        dec_ng of 64): the slab kernel skips the K steps over the padding."""
+    def conv(self, x, W: _Weights, name, *, taps, pad, groups, dgrad=False, bias=None, x_real=0, ng_out=None):
+        """``x_real``: channels per input group that can be non-zero when that is less than the 64 K columns the
+        weights hold per tap (decoder: dec_ng): the slab kernel skips the K steps over the rest. ``ng_out``: outputs
+        per group to write, that many columns apart (compact decoder layout)."""
         w = (W.dgrad if dgrad else W.fwd)[name]
         if self.fp32:
             x = self._split_a(x, (W.split_d if dgrad else W.split)[name])
         elif gemm.conv_slab_ok(x, w, taps, groups):
             return gemm.conv_slab(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias,
-                                  x_real_cols=x_real)
+                                  x_real_cols=x_real, ng_out=ng_out)
+        assert ng_out is None or ng_out == w.shape[0] // groups
         return gemm.conv_nt(x, w, taps=taps, pad=pad, groups=groups, out_dtype=self.adt, bias=bias)
 
     def wgrad(self, dy, x, out):
@@ -406,7 +413,7 @@ class PretrainEngine:
             b, t, n = dy.shape
             dy = ops.split3(dy.reshape(-1, n), 2).view(3 * b, t, n)
             x = ops.split3(x.reshape(-1, x.shape[-1]), 3).view(3 * b, t, x.shape[-1])
-        elif x.shape[-1] == groups * 64 and dy.shape[-1] // groups <= 64 and taps <= 32:
+        elif x.shape[-1] in (groups * 64, groups * 48) and dy.shape[-1] // groups <= 64 and taps <= 32:
             gemm.conv_slab_wgrad(dy, x, out, taps=taps, pad=pad, groups=groups)
             return
         gemm.conv_wgrad_tn(dy, x, out, taps=taps, pad=pad, groups=groups)
@@ -566,11 +573,13 @@ class PretrainEngine:
         dc = self.dec
         if dc.decoder_kernel % 2 == 0:
             raise NotImplementedError("even decoder kernel (SamePad trim)")
-        cfg_l = ops.RowLnCfg(self.dec_wp, 1e-5, act=1, group_width=GP, group_real=self.dec_ng)
+        cfg_l = ops.RowLnCfg(self.dec_wp, 1e-5, act=1, group_width=self.dec_gw, group_real=self.dec_ng)
+        compact = self.dec_gw != GP
         for l in range(dc.decoder_layers):
             n = ENC + f"decoder.blocks.{l}.0.weight"
             y = self.conv(x, W, n, taps=dc.decoder_kernel, pad=dc.decoder_kernel // 2, groups=dc.decoder_groups,
-                          bias=W.f32[ENC + f"decoder.blocks.{l}.0.bias"], x_real=0 if l == 0 else self.dec_ng)
+                          bias=W.f32[ENC + f"decoder.blocks.{l}.0.bias"], x_real=0 if l == 0 else self.dec_ng,
+                          ng_out=self.dec_ng if compact else None)
             res = x if l > 0 else None  # layer 0 changes the channel count: no residual
             act, m, r = ops.rowln_fwd(cfg_l, y, post=res, save_stats=save is not None)
             if save is not None:
@@ -807,7 +816,8 @@ class PretrainEngine:
             self.conv_wgrad(dy, s.x, self.gpacked[n + "|F"], taps=dc.decoder_kernel, pad=dc.decoder_kernel // 2,
                             groups=dc.decoder_groups)
             dxin = self.conv(dy, W, n, taps=dc.decoder_kernel, pad=dc.decoder_kernel - 1 - dc.decoder_kernel // 2,
-                             groups=dc.decoder_groups, dgrad=True, x_real=self.dec_ng)
+                             groups=dc.decoder_groups, dgrad=True, x_real=self.dec_ng,
+                             ng_out=self.dec_ng if (self.dec_gw != GP and l > 0) else None)
             if s.res:  # y = act(...) + x: the residual passes dx straight through
                 dxin = self._add(dxin, dx)
             dx = dxin

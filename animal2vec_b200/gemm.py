@@ -354,29 +354,36 @@ def gathered_conv_wgrad_tn(dy: torch.Tensor, xg: torch.Tensor, out: torch.Tensor
 
 
 def conv_slab_ok(x: torch.Tensor, w: torch.Tensor, taps: int, groups: int) -> bool:
-    """The slab kernel covers bf16 tap convs with 64-channel groups and <= 64 outputs per group."""
+    """The slab kernel covers bf16 tap convs with 64-channel groups (or compact 48-of-64 groups, see :func:`conv_slab`)
+    and <= 64 outputs per group."""
     if x.dtype != torch.bfloat16 or x.dim() != 3 or taps > 32:
         return False
     cin, nout = x.shape[-1], w.shape[0]
-    return cin == groups * 64 and nout // groups <= 64 and w.shape[1] == taps * 64
+    return cin in (groups * 64, groups * 48) and nout // groups <= 64 and w.shape[1] == taps * 64
 
 
 def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: int,
               out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-              bias: Optional[torch.Tensor] = None, x_real_cols: int = 0) -> torch.Tensor:
+              bias: Optional[torch.Tensor] = None, x_real_cols: int = 0, ng_out: Optional[int] = None) -> torch.Tensor:
     """Same operator as :func:`conv_nt` (64-channel groups), every activation row read once per tile. ``x_real_cols``:
-    channels per 64-wide input group that can be non-zero (group-padded layouts); the K steps over the rest are skipped."""
+    channels per 64-wide input group that can be non-zero (group-padded layouts); the K steps over the rest are skipped.
+    Compact group-padded layouts: ``x`` may store its groups ``x_real_cols`` = 48 channels apart (x.shape[-1] =
+    groups * 48; the weights keep 64 K columns per tap), and ``ng_out`` < w.shape[0] // groups writes only the first
+    ``ng_out`` outputs of every group, ``ng_out`` columns apart (the weight rows beyond are padding)."""
     bsz, t, cin = x.shape
     assert x.is_contiguous() and w.is_contiguous() and w.dtype == torch.bfloat16
-    nout = w.shape[0]
-    ng = nout // groups
+    wrows = w.shape[0] // groups
+    ng = ng_out or wrows
+    nout = groups * ng
+    xg = cin // groups
+    assert xg == 64 or (xg == x_real_cols and xg % 16 == 0), (xg, x_real_cols)
     if out is None:
         out = torch.empty(bsz, t, nout, device=x.device, dtype=out_dtype or torch.bfloat16)
     assert out.is_contiguous() and out.shape == (bsz, t, nout)
     d = L.ConvDesc()
     d.x, d.w, d.y = x.data_ptr(), w.data_ptr(), out.data_ptr()
     d.batch, d.T, d.groups, d.taps, d.pad = bsz, t, groups, taps, pad
-    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, 64, ng, ng
+    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, xg, wrows, ng
     d.ldx, d.ldw, d.ldy = cin, w.shape[1], nout
     d.y_dtype = L.dtype_code(out)
     d.bias = bias.data_ptr() if bias is not None else None
@@ -394,27 +401,31 @@ def conv_slab(x: torch.Tensor, w: torch.Tensor, *, taps: int, pad: int, groups: 
     L.check(L.load().a2v_conv_slab_fwd(C.byref(d), L.stream_ptr()), "a2v_conv_slab_fwd")
     if tl is not None:
         e1.record()
-        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps, "slab"))
+        tl.append((e0, e1, 2.0 * bsz * t * nout * (x_real_cols or 64) * taps, "slab"))
     return out
 
 
 def conv_slab_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, taps: int, pad: int, groups: int) -> torch.Tensor:
     """Same contract as :func:`conv_wgrad_tn` (transposed (G*taps*64, Ng) fp32 output) for 64-channel groups:
-    one x slab per 64-row k-block serves all taps of a 16-tap block."""
+    one x slab per 64-row k-block serves all taps of a 16-tap block. Compact group-padded layouts: ``x`` with its groups
+    48 channels apart (rows c >= 48 of every 64-row tap block of ``out`` are scratch) and / or ``dy`` with fewer columns
+    per group than ``out`` has (the columns beyond are left untouched)."""
     bsz, t, cin = x.shape
     nout = dy.shape[-1]
     ng = nout // groups
-    assert cin == groups * 64 and ng <= 64 and dy.shape[:2] == x.shape[:2] and dy.is_contiguous() and x.is_contiguous()
-    assert out.dtype == torch.float32 and out.shape == (groups * taps * 64, ng) and out.is_contiguous()
+    xg = cin // groups
+    assert xg in (64, 48) and ng <= 64 and dy.shape[:2] == x.shape[:2] and dy.is_contiguous() and x.is_contiguous()
+    assert out.dtype == torch.float32 and out.shape[0] == groups * taps * 64 and out.shape[1] >= ng and out.is_contiguous()
     d = L.ConvDesc()
     d.x, d.w, d.y = x.data_ptr(), dy.data_ptr(), None
     d.batch, d.T, d.groups, d.taps, d.pad = bsz, t, groups, taps, pad
-    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, 64, ng, ng
-    d.ldx, d.ldw, d.ldy = cin, nout, ng
+    d.ng, d.x_group_cols, d.w_group_rows, d.y_group_cols = ng, xg, ng, ng
+    d.x_real_cols = xg if xg < 64 else 0
+    d.ldx, d.ldw, d.ldy = cin, nout, out.shape[1]
     d.y_dtype = L.F32
     L.require_device(x)
     L.launch_count += 1
-    fn = lambda: L.check(L.load().a2v_conv_slab_wgrad(C.byref(d), C.c_void_p(out.data_ptr()), C.c_int64(ng),
+    fn = lambda: L.check(L.load().a2v_conv_slab_wgrad(C.byref(d), C.c_void_p(out.data_ptr()), C.c_int64(out.shape[1]),
                                                       L.stream_ptr()), "a2v_conv_slab_wgrad")
     tl = L.gemm_timeline
     if L.op_timeline is not None:
@@ -424,7 +435,7 @@ def conv_slab_wgrad(dy: torch.Tensor, x: torch.Tensor, out: torch.Tensor, *, tap
         e0.record()
         fn()
         e1.record()
-        tl.append((e0, e1, 2.0 * bsz * t * nout * 64 * taps, "slab"))
+        tl.append((e0, e1, 2.0 * bsz * t * nout * xg * taps, "slab"))
     else:
         fn()
     return out

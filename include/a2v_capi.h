@@ -134,7 +134,8 @@ typedef struct {
     void* y;
     int batch, T, groups, taps, pad;
     int ng;               /* outputs per group, <= 64 */
-    int x_group_cols;     /* must be 64 */
+    int x_group_cols;     /* channel distance between the groups of x: 64, or a smaller multiple of 16 with x_real_cols <=
+                             x_group_cols (compact group-padded layout; the 64-channel box then overlaps the next group) */
     int w_group_rows;
     int y_group_cols;
     int64_t ldx, ldw, ldy;
