@@ -34,6 +34,16 @@ constexpr int G2_EPI_BYTES = 8 * 32 * G2_EPI_PITCH;
 constexpr int G2_BIAS_BYTES = 8 * 128 * 4;
 constexpr int G2_SMEM = G2_STAGES * G2_STAGE_BYTES + G2_BAR_BYTES + G2_EPI_BYTES + G2_BIAS_BYTES + 1024;
 constexpr int G2_EPI_BIAS = 1, G2_EPI_PREACT = 2, G2_EPI_GELU = 4, G2_EPI_DGELU = 8, G2_EPI_RES = 16;
+// Epilogues with GELU / GELU' arithmetic (and a second stored or loaded tile) take longer per tile than the MMAs of the
+// next tile when 8 warps share them (fc1 forward 0.35 ms against 0.26 ms plain): those variants run 16 epilogue warps
+// (two 32-column chunks each) and pay for the extra staging with one pipeline stage.
+__host__ __device__ constexpr bool g2_heavy(int epi) { return (epi & (G2_EPI_GELU | G2_EPI_DGELU)) != 0; }
+__host__ __device__ constexpr int g2_epi_warps(int epi) { return g2_heavy(epi) ? 16 : 8; }
+__host__ __device__ constexpr int g2_stages(int epi) { return g2_heavy(epi) ? 5 : G2_STAGES; }
+__host__ __device__ constexpr int g2_threads(int epi) { return 64 + 32 * g2_epi_warps(epi); }
+__host__ __device__ constexpr int g2_smem(int epi) {
+    return g2_stages(epi) * G2_STAGE_BYTES + G2_BAR_BYTES + g2_epi_warps(epi) * 32 * G2_EPI_PITCH + G2_BIAS_BYTES + 1024;
+}
 
 struct Gemm2Params {
     int M, N, kblocks;
@@ -99,17 +109,19 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(G2_THREADS, 1)
+__global__ void __launch_bounds__(g2_threads(EPI), 1)
 gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Gemm2Params p) {
+    constexpr int STAGES = g2_stages(EPI);
+    constexpr int EW = g2_epi_warps(EPI);  // epilogue warps per CTA
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + G2_STAGES;
-    uint64_t* tfull_bar = empty_bar + G2_STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * G2_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    uint8_t* epi_stage = smem + G2_STAGES * G2_STAGE_BYTES + G2_BAR_BYTES;
-    float* bias_stage = reinterpret_cast<float*>(epi_stage + G2_EPI_BYTES);
+    uint8_t* epi_stage = smem + STAGES * G2_STAGE_BYTES + G2_BAR_BYTES;
+    float* bias_stage = reinterpret_cast<float*>(epi_stage + EW * 32 * G2_EPI_PITCH);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -119,13 +131,13 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int i = 0; i < G2_STAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps of each CTA of the pair (used in the leader only)
+            mbar_init(&tempty_bar[i], 2 * EW);  // the epilogue warps of both CTAs of the pair (used in the leader only)
         }
         mbar_fence_init();
         fence_proxy_async();
@@ -154,7 +166,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     if (leader) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);  // both CTAs' halves
                     tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * G2_BK, m2 * (2 * G2_BM) + (int)rank * G2_BM, 0);
                     tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * G2_BK, n_tile * G2_BN + (int)rank * (G2_BN / 2), 0);
-                    if (++stage == G2_STAGES) {
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -184,7 +196,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         umma2_bf16(tmem_d, umma_smem_desc(a_base + k * 32, 0, 1024), umma_smem_desc(b_base + k * 32, 0, 1024),
                                    idesc, (kb > 0 || k > 0) ? 1u : 0u);
                     umma2_commit(&empty_bar[stage]);
-                    if (++stage == G2_STAGES) {
+                    if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -202,7 +214,7 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // of gemm_sm100.cu: TMEM-native arithmetic (thread = row), bf16 staging transpose, 16-byte stores
         const int q = warp & 3;
         const int ew = warp - 2;
-        constexpr int CPW = 4;  // 32-column chunks per warp (half of the 256 columns)
+        constexpr int CPW = 32 / EW;  // 32-column chunks per warp: 8 warps take half of the 256 columns each, 16 a quarter
         const int c_begin = (ew >> 2) * CPW;
         const uint32_t st = smem_u32(epi_stage + ew * (32 * G2_EPI_PITCH));
         const int rrow = lane & 7, rchunk = lane >> 3;
@@ -217,7 +229,8 @@ gemm2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int cbase = n_tile * G2_BN + c_begin * 32;
             float* bs = bias_stage + ew * (CPW * 32);
             if (EPI & G2_EPI_BIAS) {
-                *reinterpret_cast<float4*>(bs + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + lane);
+                if (lane < CPW * 8)
+                    *reinterpret_cast<float4*>(bs + lane * 4) = __ldg(reinterpret_cast<const float4*>(p.bias + cbase) + lane);
                 __syncwarp();
             }
             constexpr bool DGELU = (EPI & G2_EPI_DGELU) != 0;
@@ -522,14 +535,14 @@ static int g2_make_map(CUtensorMap* m, const a2v_operand& o, int box_rows = 128)
 template <int EPI>
 static int g2_launch(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm2Params& p, cudaStream_t st) {
     auto kern = gemm2cta_kernel<EPI>;
-    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (size_t)G2_SMEM) != A2V_OK) return A2V_ERR_CUDA;
+    if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (size_t)g2_smem(EPI)) != A2V_OK) return A2V_ERR_CUDA;
     int pairs = a2v_num_sms() / 2;
     if (pairs > p.num_tiles) pairs = p.num_tiles;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(G2_THREADS);
-    cfg.dynamicSmemBytes = G2_SMEM;
+    cfg.blockDim = dim3(g2_threads(EPI));
+    cfg.dynamicSmemBytes = g2_smem(EPI);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
