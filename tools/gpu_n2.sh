@@ -6,8 +6,8 @@ timeout 600 python -m pytest tests/test_trainer_gpu.py tests/test_ddp_cpu.py -q 
 grep -E "passed|failed|FAILED|^E  |skipped" gpurun_out/n2_tests.log | head
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/n2_bench.json 2> gpurun_out/n2_bench.err
 tail -c 1500 gpurun_out/n2_bench.json; tail -5 gpurun_out/n2_bench.err
-A2V_GRAD_BF16=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/n2_bench_fp32buckets.json 2> gpurun_out/n2_bench_fp32.err
 python -c "
 import json
-for f in ('n2_bench','n2_bench_fp32buckets'):
-    d=json.load(open('gpurun_out/'+f+'.json')); print(f, d['value'], d['ms_per_step'], d['n_gpus'])"
+for line in open('gpurun_out/n2_bench.json'):
+    if line.startswith('{'):
+        d=json.loads(line); print('N2', d['value'], d['ms_per_step'], d['n_gpus'], d['e2e']['value'])"
