@@ -347,6 +347,12 @@ struct ConvWgradParams {
     int nt[2];           // M tiles per tap block
     int splits[2];       // K splits per tap block
     int num_tiles;
+    // 5..8 taps: a SECOND copy of the x slab, loaded 4 rows further down, is the second 64-wide M chunk of every tile, so
+    // M tile i pairs tap i with tap i + 4 (pairing with tap i + 8 -- the same slab 8 rows down -- would leave half of
+    // every 128-row MMA on taps that do not exist: the 7-tap decoder layers ran at half rate)
+    int pair_off;        // 8, or 4 with the second slab copy
+    int stages;          // pipeline stages (8, or 6 with the second slab copy)
+    int stage_bytes;
 };
 
 __global__ void __launch_bounds__(CS_THREADS, 1)
@@ -354,7 +360,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                        const ConvWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CW_STAGES * CW_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * p.stage_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + CW_STAGES;
     uint64_t* tfull = empty_bar + CW_STAGES;  // [1]
@@ -403,11 +409,13 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
                 const int b = kb / p.kb_per_batch;
                 const int r0 = (kb - b * p.kb_per_batch) * 64;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sx = smem + stage * CW_STAGE_BYTES;
-                mbar_expect_tx(&full_bar[stage], CW_STAGE_BYTES);
+                uint8_t* sx = smem + stage * p.stage_bytes;
+                mbar_expect_tx(&full_bar[stage], (uint32_t)p.stage_bytes);
                 tma_load_3d(sx, &tmX, &full_bar[stage], g * p.x_group_cols, r0 + tb * 16 - p.pad, b);
-                tma_load_3d(sx + CW_SLAB_BYTES, &tmDy, &full_bar[stage], g * p.dy_group_cols, r0, b);
-                if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
+                if (p.pair_off == 4)
+                    tma_load_3d(sx + CW_SLAB_BYTES, &tmX, &full_bar[stage], g * p.x_group_cols, r0 + 4 - p.pad, b);
+                tma_load_3d(sx + p.stage_bytes - CW_DY_BYTES, &tmDy, &full_bar[stage], g * p.dy_group_cols, r0, b);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
         __syncwarp();
@@ -419,19 +427,21 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t sx = smem_u32(smem + stage * CW_STAGE_BYTES);
-                const uint32_t sd = sx + CW_SLAB_BYTES;
+                const uint32_t sx = smem_u32(smem + stage * p.stage_bytes);
+                const uint32_t sd = sx + (uint32_t)(p.stage_bytes - CW_DY_BYTES);
+                // A: M-major, 16 K rows per step (2048 B); M chunk 1 = 8 rows (1024 B) below chunk 0, or the same rows of
+                // the second slab copy (which starts 4 x rows later)
+                const uint32_t lbo = p.pair_off == 4 ? (uint32_t)CW_SLAB_BYTES : 1024u;
                 for (int i = 0; i < nt; ++i) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        // A: M-major, 16 K rows per step (2048 B), M chunk 1 = 8 rows (1024 B) below chunk 0
-                        const uint64_t da = umma_smem_desc(sx + (uint32_t)i * 128u + k * 2048, 1024, 1024);
+                        const uint64_t da = umma_smem_desc(sx + (uint32_t)i * 128u + k * 2048, lbo, 1024);
                         const uint64_t db = umma_smem_desc(sd + k * 2048, 0, 1024);
                         umma_bf16(tmem_base + i * 64, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&empty_bar[stage]);
-                if (++stage == CW_STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(tfull);
         }
@@ -443,7 +453,7 @@ conv_slab_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         tc_fence_after();
 #pragma unroll 1
         for (int i = 0; i < nt; ++i) {
-            const int tap = tb * 16 + i + (q >= 2 ? 8 : 0);
+            const int tap = tb * 16 + i + (q >= 2 ? p.pair_off : 0);
             const int ch0 = (q & 1) * 32;
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
@@ -592,9 +602,13 @@ extern "C" int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t l
     p.out = out; p.ldo = ldo;
     p.kb_per_batch = ceil_div(d->T, 64);
     p.n_tb = ceil_div(d->taps, 16);
+    const bool narrow = d->taps >= 5 && d->taps <= 8;
+    p.pair_off = narrow ? 4 : 8;
+    p.stages = narrow ? 6 : CW_STAGES;
+    p.stage_bytes = (narrow ? 2 : 1) * CW_SLAB_BYTES + CW_DY_BYTES;
     for (int tb = 0; tb < 2; ++tb) {
         const int rem = d->taps - 16 * tb;
-        p.nt[tb] = tb < p.n_tb ? (rem < 8 ? rem : 8) : 0;
+        p.nt[tb] = tb < p.n_tb ? (rem < p.pair_off ? rem : p.pair_off) : 0;
         p.splits[tb] = 0;
     }
     // K splits per tap block: fill the SMs once, minimise the longest CTA (work ~ M tiles / splits)
@@ -622,7 +636,7 @@ extern "C" int a2v_conv_slab_wgrad(const a2v_conv_desc* d, float* out, int64_t l
     int rc;
     if ((rc = cs_make_map(&tx, d->x, d->ldx, d->T, d->batch, d->ldx, CW_SLAB_ROWS, "x")) != A2V_OK) return rc;
     if ((rc = cs_make_map(&tdy, d->w, d->ldw, d->T, d->batch, d->ldw, 64, "dy")) != A2V_OK) return rc;
-    const int smem = CW_STAGES * CW_STAGE_BYTES + 256 + CS_EPI_BYTES + 1024;
+    const int smem = p.stages * p.stage_bytes + 256 + CS_EPI_BYTES + 1024;
     if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(conv_slab_wgrad_kernel), (size_t)smem) != A2V_OK) return A2V_ERR_CUDA;
     conv_slab_wgrad_kernel<<<p.num_tiles, CS_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tdy, p);
     return a2v_check_launch("conv_slab_wgrad");
