@@ -7,6 +7,7 @@
 //   autograd of the conv w.r.t. the filters -> a2v_sinc_conv_wgrad
 // Output layout is channels-last (B, N, Cpad) with Cpad = 128 (channel 127 is a zero pad) so
 // that the next stage (LayerNorm over channels, then a K = 10*128 GEMM) reads contiguous rows.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/a2v_capi.h"
 
@@ -138,6 +139,175 @@ __global__ void __launch_bounds__(256) sinc_conv_fwd_kernel(const float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same convolution on tcgen05 (bf16 output): per 128-sample tile the Toeplitz operand
+//   A[t][k] = x[b, reflect(t0 + t + k - K/2)]        (128 x 128, K padded with zero filter taps)
+// is built in shared memory and multiplied with the (128 channels x 128 taps) filter matrix. Both operands are split
+// into bf16 hi + lo pieces and three products accumulate in fp32 (hi*hi + hi*lo + lo*hi: the band-pass sums cancel
+// heavily, single bf16 operands would cost ~1e-2 of the output): 24 MMAs of 128 x 128 x 16 per tile, ~1 500 tensor
+// clocks against ~16 000 FMA-pipe clocks of the CUDA-core kernel above (which stays for the fp32 validation mode).
+// 256 threads: everyone builds the next tile's operand while the tensor pipe works on the current one; thread 0
+// issues; warps 0-3 / 4-7 drain columns 0-63 / 64-127 of the double-buffered TMEM accumulator.
+// ------------------------------------------------------------------------------------------
+constexpr int STC_A_BYTES = 2 * 2 * 16384;     // hi / lo x two 64-tap halves, each a 128-row 128B-swizzled tile
+constexpr int STC_SM_B = 0;                    // filters: hi (2 x 16 KB), lo (2 x 16 KB)
+constexpr int STC_SM_A = 65536;                // two operand buffers
+constexpr int STC_SM_X = STC_SM_A + 2 * STC_A_BYTES;   // fp32 samples of a tile: 128 + 127 (+ pad)
+constexpr int STC_SM_BAR = STC_SM_X + 2 * 1024;
+constexpr int STC_SMEM_TOTAL = STC_SM_BAR + 64 + 1024;
+
+// element (row r, tap k) of a [128][64] bf16 tile with 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+__device__ __forceinline__ uint32_t stc_chunk_off(int r, int chunk) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+__global__ void __launch_bounds__(256, 1) sinc_conv_fwd_tc_kernel(const float* __restrict__ x, const float* __restrict__ filt,
+                                                                  bf16* __restrict__ y, int N, int K, int tiles_per_clip,
+                                                                  int num_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + STC_SM_BAR);  // [2]: accumulator buffer i complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = K / 2;
+
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    // filters -> hi / lo bf16 tiles (row = channel, K-major); thread: channel tid & 127, tap half tid >> 7
+    const int nsteps = (K + 15) >> 4;  // K steps of 16 taps (taps beyond K are zero: not multiplied at all)
+    if ((tid >> 7) * 64 < K) {
+        const int c = tid & 127, h = tid >> 7;
+        const float* fr = filt + (long long)c * K;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k0 = h * 64 + ch * 8 + 2 * e;
+                const float a = k0 < K ? fr[k0] : 0.f, b = k0 + 1 < K ? fr[k0 + 1] : 0.f;
+                const float ah = __bfloat162float(__float2bfloat16_rn(a)), bh = __bfloat162float(__float2bfloat16_rn(b));
+                hi[e] = pack_bf16x2(ah, bh);
+                lo[e] = pack_bf16x2(a - ah, b - bh);
+            }
+            const uint32_t o = stc_chunk_off(c, ch);
+            *reinterpret_cast<uint4*>(smem + STC_SM_B + h * 16384 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(smem + STC_SM_B + 32768 + h * 16384 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
+
+    // operand of tile `tile` into buffer `buf`: stage the 255 samples, then thread (row tid & 127, tap half tid >> 7)
+    // writes its 64 taps as hi / lo bf16
+    auto build = [&](int tile, int buf) {
+        const int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * 128;
+        const float* xb = x + (long long)b * N;
+        float* sx = reinterpret_cast<float*>(smem + STC_SM_X + buf * 1024);
+        if (tid < 255) {
+            const int j = t0 + tid - half;
+            sx[tid] = (j < N + half) ? xb[reflect_index(j, N)] : 0.f;
+        }
+        __syncthreads();
+        const int r = tid & 127, h = tid >> 7;
+        uint8_t* ab = smem + STC_SM_A + buf * STC_A_BYTES;
+#pragma unroll 2
+        for (int ch = 0; ch < (h * 64 < K ? 8 : 0); ++ch) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k0 = h * 64 + ch * 8 + 2 * e;
+                const float a = sx[r + k0], c = k0 + 1 < 128 ? sx[(r + k0 + 1) < 255 ? r + k0 + 1 : 254] : 0.f;
+                const float ah = __bfloat162float(__float2bfloat16_rn(a)), ch_ = __bfloat162float(__float2bfloat16_rn(c));
+                hi[e] = pack_bf16x2(ah, ch_);
+                lo[e] = pack_bf16x2(a - ah, c - ch_);
+            }
+            const uint32_t o = stc_chunk_off(r, ch);
+            *reinterpret_cast<uint4*>(ab + h * 16384 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(ab + 32768 + h * 16384 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();  // generic-proxy writes -> the tensor pipe's async-proxy reads
+    };
+    auto issue = [&](int buf) {  // thread 0, after the __syncthreads that follows build(): 3 x 8 products of 128 x 128 x 16
+        const uint32_t a0 = smem_u32(smem + STC_SM_A + buf * STC_A_BYTES), b0 = smem_u32(smem + STC_SM_B);
+        const uint32_t td = tmem_base + buf * 128;
+#pragma unroll
+        for (int pr = 0; pr < 3; ++pr) {
+            const uint32_t aa = a0 + (pr == 2 ? 32768u : 0u), bb = b0 + (pr == 1 ? 32768u : 0u);  // hi*hi, hi*lo, lo*hi
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                if (s >= nsteps) break;
+                const uint32_t ko = (uint32_t)(s >> 2) * 16384u + (uint32_t)(s & 3) * 32u;
+                umma_bf16(td, umma_smem_desc(aa + ko, 0, 1024), umma_smem_desc(bb + ko, 0, 1024), idesc,
+                          (pr > 0 || s > 0) ? 1u : 0u);
+            }
+        }
+        umma_commit(&bar_mma[buf]);
+    };
+
+    int it = 0;
+    const int first = blockIdx.x;
+    if (first < num_tiles) {
+        build(first, 0);
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue(0);
+        }
+    }
+    for (int tile = first; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int next = tile + gridDim.x;
+        if (next < num_tiles) {
+            // the other accumulator buffer was drained in the previous iteration (the __syncthreads inside build orders it)
+            build(next, buf ^ 1);
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue(buf ^ 1);
+            }
+        }
+        mbar_wait(&bar_mma[buf], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        // epilogue: thread = output row (TMEM lane), 64 of the 128 channels per warp group
+        const int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * 128;
+        const int r = (warp & 3) * 32 + lane, t = t0 + r;
+        const int cbase = (warp >> 2) * 64;
+        bf16* yrow = y + ((long long)b * N + (t < N ? t : 0)) * SINC_CPAD + cbase;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + buf * 128 + cbase + c * 32, raw);
+            tmem_ld_wait();
+            if (t < N) {
+#pragma unroll
+                for (int d = 0; d < 32; d += 8) {
+                    uint4 v;
+                    v.x = pack_bf16x2(__uint_as_float(raw[d]), __uint_as_float(raw[d + 1]));
+                    v.y = pack_bf16x2(__uint_as_float(raw[d + 2]), __uint_as_float(raw[d + 3]));
+                    v.z = pack_bf16x2(__uint_as_float(raw[d + 4]), __uint_as_float(raw[d + 5]));
+                    v.w = pack_bf16x2(__uint_as_float(raw[d + 6]), __uint_as_float(raw[d + 7]));
+                    *reinterpret_cast<uint4*>(yrow + c * 32 + d) = v;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem_base);
+    }
+}
+
 // dfilt[c][k] += sum_{b,t} dy[b, t, c] * x[b, reflect(t + k - K/2)]
 // grid (chunks, B); each block walks its chunk of time steps in tiles of SINC_TT.
 template <typename TI>
@@ -260,12 +430,23 @@ extern "C" int a2v_sinc_conv_fwd(int out_dtype, const float* x, const float* fil
     dim3 grid(ceil_div(N, SINC_TT), B);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (out_dtype == A2V_F32) {
-        static bool cfg = false;
-        if (!cfg) { cudaFuncSetAttribute(sinc_conv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_fwd_kernel<float>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_fwd_kernel<float><<<grid, 256, smem, st>>>(x, filters, (float*)y, N, K);
     } else {
-        static bool cfg = false;
-        if (!cfg) { cudaFuncSetAttribute(sinc_conv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        static int use_tc = -1;  // A2V_SINC_TC=0: CUDA-core kernel for the bf16 output as well
+        if (use_tc < 0) {
+            const char* e = getenv("A2V_SINC_TC");
+            use_tc = (e == nullptr || e[0] != '0') ? 1 : 0;
+        }
+        if (use_tc == 1 && K <= 128 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+            if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_fwd_tc_kernel), STC_SMEM_TOTAL) != A2V_OK)
+                return A2V_ERR_CUDA;
+            const int tiles_per_clip = ceil_div(N, 128), num_tiles = tiles_per_clip * B;
+            const int g = num_tiles < a2v_num_sms() ? num_tiles : a2v_num_sms();
+            sinc_conv_fwd_tc_kernel<<<g, 256, STC_SMEM_TOTAL, st>>>(x, filters, (bf16*)y, N, K, tiles_per_clip, num_tiles);
+            return a2v_check_launch("sinc_conv_fwd_tc");
+        }
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_fwd_kernel<bf16>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_fwd_kernel<bf16><<<grid, 256, smem, st>>>(x, filters, (bf16*)y, N, K);
     }
     return a2v_check_launch("sinc_conv_fwd");
@@ -284,12 +465,10 @@ extern "C" int a2v_sinc_conv_wgrad(int dy_dtype, const float* x, const void* dy,
     dim3 grid(ceil_div(N, steps), B);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dy_dtype == A2V_F32) {
-        static bool cfg = false;
-        if (!cfg) { cudaFuncSetAttribute(sinc_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_wgrad_kernel<float>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_wgrad_kernel<float><<<grid, 256, smem, st>>>(x, (const float*)dy, dfilters, N, K, steps);
     } else {
-        static bool cfg = false;
-        if (!cfg) { cudaFuncSetAttribute(sinc_conv_wgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+        if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_wgrad_kernel<bf16>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_wgrad_kernel<bf16><<<grid, 256, smem, st>>>(x, (const bf16*)dy, dfilters, N, K, steps);
     }
     return a2v_check_launch("sinc_conv_wgrad");

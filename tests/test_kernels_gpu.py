@@ -573,6 +573,27 @@ def test_sinc():
     assert _rel(dband, band.grad.view(-1)) < 2e-3, _rel(dband, band.grad.view(-1))
 
 
+@pytest.mark.parametrize("k,n", [(63, 3000), (125, 1100), (31, 257)])
+def test_sinc_conv_forward_on_tensor_cores(k, n):
+    """bf16 output path: Toeplitz operand x filter matrix on tcgen05 with hi + lo bf16 splits of both operands (three
+    products); against fp32 conv1d with reflect padding, ragged lengths, tap counts below / above one 64-tap half."""
+    from animal2vec_b200 import ops
+
+    b, c = 3, 127
+    x = torch.randn(b, n, device="cuda", generator=_g(1)) * 3.0
+    filt = torch.zeros(128, k, device="cuda")
+    filt[:c] = torch.randn(c, k, device="cuda", generator=_g(2)) * torch.hann_window(k, device="cuda")
+    ref = F.conv1d(F.pad(x.unsqueeze(1), (k // 2, k // 2), mode="reflect"), filt[:c].view(c, 1, k)).transpose(1, 2)
+    y16 = ops.sinc_conv_fwd(x, filt, torch.bfloat16)
+    y32 = ops.sinc_conv_fwd(x, filt, torch.float32)
+    assert _rel(y32[..., :c], ref) < 1e-5
+    assert y16[..., 127].float().abs().sum().item() == 0
+    # the split products carry ~2^-17 relative operand error: the result differs from the fp32 kernel's by far less than
+    # the bf16 rounding of the output
+    assert _rel(y16[..., :c], ref) < 3e-3, _rel(y16[..., :c], ref)
+    assert _rel(y16.float(), y32.bfloat16().float()) < 1e-3, _rel(y16.float(), y32.bfloat16().float())
+
+
 @pytest.mark.parametrize("k,s,pad,c,tin", [(10, 5, 3, 128, 1000), (3, 2, 1, 512, 401), (3, 2, 1, 64, 400)])
 def test_im2col_col2im(k, s, pad, c, tin):
     from animal2vec_b200 import ops
