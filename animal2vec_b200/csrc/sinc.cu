@@ -308,6 +308,137 @@ __global__ void __launch_bounds__(256, 1) sinc_conv_fwd_tc_kernel(const float* _
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Filter gradient on tcgen05 (bf16 dy):  dfilt[c][k] += sum_{b,t} dy[b, t, c] * x[b, reflect(t + k - K/2)]
+// = dy^T (channels x time) times the Toeplitz operand (time x taps) of sinc_conv_fwd_tc_kernel. Per 128-sample tile
+// both operands sit in shared memory with the time index along the rows (MN-major for the MMA: M = channels, N = taps,
+// K = time): dy as stored (bf16), x split into hi + lo -- two products of 8 K steps, accumulated over ALL tiles of the
+// CTA in one 128 x 128 fp32 TMEM accumulator; one atomic add per (channel, tap) and CTA at the end.
+// ------------------------------------------------------------------------------------------
+constexpr int SWG_SM_DY = 0;                       // two buffers of [2 channel halves][128 t][64 c] bf16
+constexpr int SWG_SM_A = 2 * 32768;                // two buffers of hi / lo x [2 tap halves][128 t][64 k]
+constexpr int SWG_SM_X = SWG_SM_A + 2 * STC_A_BYTES;
+constexpr int SWG_SM_BAR = SWG_SM_X + 2 * 1024;
+constexpr int SWG_SMEM_TOTAL = SWG_SM_BAR + 64 + 1024;
+
+__global__ void __launch_bounds__(256, 1) sinc_conv_wgrad_tc_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                                    float* __restrict__ dfilt, int N, int K,
+                                                                    int tiles_per_clip, int num_tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + SWG_SM_BAR);  // [2]: the products reading buffer i retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int half = K / 2;
+    if (tid == 0) {
+        mbar_init(&bar_mma[0], 1);
+        mbar_init(&bar_mma[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nhalf = K > 64 ? 2 : 1;  // 64-tap halves that hold real taps (the N extent of the product)
+    const uint32_t idesc_n = umma_idesc_bf16(128, nhalf * 64, true, true);
+
+    auto build = [&](int tile, int buf) {
+        const int b = tile / tiles_per_clip, t0 = (tile - b * tiles_per_clip) * 128;
+        const float* xb = x + (long long)b * N;
+        float* sx = reinterpret_cast<float*>(smem + SWG_SM_X + buf * 1024);
+        if (tid < 255) {
+            const int j = t0 + tid - half;
+            sx[tid] = (j < N + half) ? xb[reflect_index(j, N)] : 0.f;
+        }
+        // dy tile: row t (256 B = 16 chunks of 8 channels) -> [channel half][t][64 c], 128-byte swizzle; rows beyond N: zeros
+        {
+            uint8_t* db = smem + SWG_SM_DY + buf * 32768;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = tid + 256 * i;  // 128 rows x 16 chunks
+                const int r = idx >> 4, ch = idx & 15;
+                const int t = t0 + r;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (t < N) v = *reinterpret_cast<const uint4*>(dy + ((long long)b * N + t) * SINC_CPAD + ch * 8);
+                *reinterpret_cast<uint4*>(db + (ch >> 3) * 16384 + stc_chunk_off(r, ch & 7)) = v;
+            }
+        }
+        __syncthreads();
+        const int r = tid & 127, h = tid >> 7;
+        uint8_t* ab = smem + SWG_SM_A + buf * STC_A_BYTES;
+#pragma unroll 2
+        for (int ch = 0; ch < (h * 64 < K ? 8 : 0); ++ch) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k0 = h * 64 + ch * 8 + 2 * e;
+                const float a = sx[r + k0], c = sx[r + k0 + 1 < 255 ? r + k0 + 1 : 254];
+                const float ah = __bfloat162float(__float2bfloat16_rn(a)), ch_ = __bfloat162float(__float2bfloat16_rn(c));
+                hi[e] = pack_bf16x2(ah, ch_);
+                lo[e] = pack_bf16x2(a - ah, c - ch_);
+            }
+            const uint32_t o = stc_chunk_off(r, ch);
+            *reinterpret_cast<uint4*>(ab + h * 16384 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(ab + 32768 + h * 16384 + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+    };
+    auto issue = [&](int buf, bool first) {  // dy^T x_hi + dy^T x_lo: 2 x 8 K steps of 16 time rows
+        const uint32_t a0 = smem_u32(smem + SWG_SM_DY + buf * 32768), b0 = smem_u32(smem + SWG_SM_A + buf * STC_A_BYTES);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr)
+#pragma unroll
+            for (int s = 0; s < 8; ++s)
+                umma_bf16(tmem_base, umma_smem_desc(a0 + s * 2048, 16384, 1024),
+                          umma_smem_desc(b0 + pr * 32768 + s * 2048, 16384, 1024), idesc_n, (first && pr == 0 && s == 0) ? 0u : 1u);
+        umma_commit(&bar_mma[buf]);
+    };
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) {  // the products of two tiles ago read this buffer
+            mbar_wait(&bar_mma[buf], (uint32_t)(((it >> 1) - 1) & 1));
+        }
+        build(tile, buf);
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue(buf, it == 0);
+        }
+    }
+    if (it > 0) {
+        // every product retired (commits arrive in order: the last one covers all)
+        const int last = (it - 1) & 1;
+        mbar_wait(&bar_mma[last], (uint32_t)((((it - 1) >> 1)) & 1));
+        tc_fence_after();
+        // epilogue: thread = channel (TMEM lane), warps 0-3 taps 0..63, warps 4-7 taps 64..127
+        const int c = (warp & 3) * 32 + lane;
+        const int kbase = (warp >> 2) * 64;
+        if (kbase < nhalf * 64) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t raw[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kbase + q * 32, raw);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int k = kbase + q * 32 + i;
+                    if (k < K) atomicAdd(dfilt + (long long)c * K + k, __uint_as_float(raw[i]));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<128>(tmem_base);
+    }
+}
+
 // dfilt[c][k] += sum_{b,t} dy[b, t, c] * x[b, reflect(t + k - K/2)]
 // grid (chunks, B); each block walks its chunk of time steps in tiles of SINC_TT.
 template <typename TI>
@@ -468,6 +599,19 @@ extern "C" int a2v_sinc_conv_wgrad(int dy_dtype, const float* x, const void* dy,
         if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_wgrad_kernel<float>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_wgrad_kernel<float><<<grid, 256, smem, st>>>(x, (const float*)dy, dfilters, N, K, steps);
     } else {
+        static int use_tc = -1;
+        if (use_tc < 0) {
+            const char* e = getenv("A2V_SINC_TC");
+            use_tc = (e == nullptr || e[0] != '0') ? 1 : 0;
+        }
+        if (use_tc == 1 && K <= 128 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {
+            if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_wgrad_tc_kernel), SWG_SMEM_TOTAL) != A2V_OK)
+                return A2V_ERR_CUDA;
+            const int tiles_per_clip = ceil_div(N, 128), num_tiles = tiles_per_clip * B;
+            const int g = num_tiles < a2v_num_sms() ? num_tiles : a2v_num_sms();
+            sinc_conv_wgrad_tc_kernel<<<g, 256, SWG_SMEM_TOTAL, st>>>(x, (const bf16*)dy, dfilters, N, K, tiles_per_clip, num_tiles);
+            return a2v_check_launch("sinc_conv_wgrad_tc");
+        }
         if (a2v_ensure_dynamic_smem(reinterpret_cast<const void*>(sinc_conv_wgrad_kernel<bf16>), 100 * 1024) != A2V_OK) return A2V_ERR_CUDA;
         sinc_conv_wgrad_kernel<bf16><<<grid, 256, smem, st>>>(x, (const bf16*)dy, dfilters, N, K, steps);
     }

@@ -592,6 +592,15 @@ def test_sinc_conv_forward_on_tensor_cores(k, n):
     # the bf16 rounding of the output
     assert _rel(y16[..., :c], ref) < 3e-3, _rel(y16[..., :c], ref)
     assert _rel(y16.float(), y32.bfloat16().float()) < 1e-3, _rel(y16.float(), y32.bfloat16().float())
+    # filter gradient with bf16 dy: dy^T x Toeplitz operand on tcgen05 (x split hi + lo), accumulated on top of nothing
+    dy = torch.randn(b, n, 128, device="cuda", generator=_g(3)).bfloat16()
+    dy[..., 127] = 0
+    leaf = filt[:c].clone().requires_grad_(True)
+    F.conv1d(F.pad(x.unsqueeze(1), (k // 2, k // 2), mode="reflect"), leaf.view(c, 1, k)).backward(
+        dy[..., :c].float().transpose(1, 2))
+    dfilt = ops.sinc_conv_wgrad(x, dy, k)
+    assert _rel(dfilt[:c], leaf.grad) < 1e-4, _rel(dfilt[:c], leaf.grad)
+    assert dfilt[127].abs().sum().item() == 0
 
 
 @pytest.mark.parametrize("k,s,pad,c,tin", [(10, 5, 3, 128, 1000), (3, 2, 1, 512, 401), (3, 2, 1, 64, 400)])
