@@ -347,8 +347,8 @@ def run_b200(args):
                      "other_tensor_kernels": {
                          k: {"ms_per_step": v[0] / args.steps, "tflops_executed": v[1] / (v[0] / 1e3) / 1e12 if v[0] else None,
                              "launches": v[2], "share_of_step": v[0] / ms_total,
-                             "note": ("conv_slab_fwd / conv_slab_wgrad (grouped stride-1 convs); executed FLOPs count the decoder's "
-                                      "48-wide groups as 64 (x1.33 of algorithmic there), exact for the positional convs")
+                             "note": ("conv_slab_fwd / conv_slab_wgrad (grouped stride-1 convs); algorithmic FLOPs (the decoder's "
+                                      "48-channel groups counted 48 wide; its first layer reads 64-channel groups)")
                              if k == "slab" else "gemm_tcgen05_kernel tap-loop / grouped launches"}
                          for k, v in fam.items() if k != "linear"}},
         "step_tensor_frac": (flop_clip * value / world / 1e12 / peaks["tflops_sustained"]) if flop_clip else None,
